@@ -1,0 +1,94 @@
+/* libjbsim -- C-ABI of the B200-native batched Jitterbug simulator.
+ *
+ * Drop-in boundary.  The reference reaches its physics through dm_control's ctypes binding of MuJoCo
+ * (jitterbug_dmc/jitterbug.py:46 `mjlib`, :81 `Physics.from_xml_string`, :84-90 `control.Environment`); one
+ * `env.step(a)` is `task.before_step` -> 50 x (`mj_step2`; `mj_step1`) -> `task.get_reward` -> `task.get_observation`.
+ * Each entry point below names the reference interface it replaces.  All functions return 0 on success, non-zero on
+ * error (message via jb_last_error()).  Pointers with the `_dev` suffix are device pointers on the simulator's
+ * device that the caller owns (e.g. torch tensor storage); `_host` pointers are host memory.  Work is enqueued on the
+ * `stream` argument (a cudaStream_t passed as void*; NULL = default stream); there are no hidden synchronisations
+ * except in the `_host` convenience calls, which synchronise the stream before returning.  A JbSim is bound to one
+ * device and is not thread-safe.  There is no CPU fallback: without a CUDA device jb_sim_create fails.
+ */
+#ifndef JBSIM_H
+#define JBSIM_H
+
+#include <stdint.h>
+#include "../jitterbug_b200/csrc/jb_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct JbSim JbSim;
+
+/* dm_env.StepType values written to step_type arrays */
+enum { JB_STEP_FIRST = 0, JB_STEP_MID = 1, JB_STEP_LAST = 2 };
+
+typedef struct {
+  int num_envs;            /* environments simulated by this handle (this rank's shard) */
+  int device;              /* CUDA device ordinal */
+  int n_sub_steps;         /* physics sub-steps per control step: round(control_timestep / timestep) = 50 */
+  int step_limit;          /* control steps per episode: time_limit / control_timestep = 1000; <= 0: no limit */
+  int random_pose;         /* Jitterbug(random_pose=True): random initial tilt (jitterbug.py:653-664) */
+  int obs_stride;          /* floats per env in observation buffers (>= widest task in the batch, max 19) */
+  uint64_t seed;           /* Philox key */
+  uint32_t env_id_offset;  /* global id of env 0 of this shard: Philox streams are keyed by global env id */
+  uint32_t pad;
+} JbSimConfig;
+
+/* Replaces Physics.from_xml_string + control.Environment construction (jitterbug.py:81-90).
+ * `models`: n_models == 1 (shared model, kept in constant memory) or n_models == num_envs (per-env augmented models,
+ * augmented_jitterbug.py:95-267).  `task_ids_host`: num_envs task ids (JB_TASK_*), or NULL for all move_from_origin. */
+int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
+                  const int32_t* task_ids_host);
+void jb_sim_destroy(JbSim* sim);
+
+/* Replaces control.Environment.reset() -> task.initialize_episode (jitterbug.py:601-666) + get_observation.
+ * `mask_dev`: num_envs bytes, non-zero = reset that env; NULL = reset all.  Writes obs for the reset envs. */
+int jb_sim_reset(JbSim* sim, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Replaces control.Environment.step(action) for every env in lock-step: set ctrl, n_sub_steps physics steps,
+ * reward, observation, step counting.  An env whose previous step returned LAST (or that was never reset) is reset
+ * instead, its action ignored, FIRST returned with reward 0 (dm_control returns reward None there).
+ * actions_dev[num_envs]; obs_dev[num_envs * obs_stride]; reward_dev[num_envs]; step_type_dev[num_envs]. */
+int jb_sim_step(JbSim* sim, const float* actions_dev, float* obs_dev, float* reward_dev, int32_t* step_type_dev,
+                void* stream);
+
+/* Same through host buffers (the reference's numpy in / numpy out call shape): H2D of actions, step, D2H of
+ * obs/reward/step_type through pinned staging, then stream synchronise. */
+int jb_sim_step_host(JbSim* sim, const float* actions_host, float* obs_host, float* reward_host,
+                     int32_t* step_type_host, void* stream);
+
+/* heuristic_policies.* (heuristic_policies.py:6-136) evaluated on device from an observation buffer. */
+int jb_sim_heuristic_actions(JbSim* sim, const float* obs_dev, float* actions_dev, void* stream);
+
+/* physics.data.qpos / qvel / qacc_warmstart access (`physics.named.data.qpos[...]`, jitterbug.py:182, :212, :661).
+ * Row-major [num_envs][16|15|15] device buffers, MuJoCo ordering.  NULL pointers are skipped. */
+int jb_sim_get_state(JbSim* sim, float* qpos_dev, float* qvel_dev, float* warm_dev, void* stream);
+int jb_sim_set_state(JbSim* sim, const float* qpos_dev, const float* qvel_dev, const float* warm_dev, void* stream);
+/* target pose per env: [num_envs][4] = x, y, quat_w, quat_z (model.body_pos / body_quat["target"], jitterbug.py:613-648) */
+int jb_sim_get_target(JbSim* sim, float* target_dev, void* stream);
+int jb_sim_set_target(JbSim* sim, const float* target_dev, void* stream);
+/* episode bookkeeping per env: step counts; setting also clears the "reset on next step" flag */
+int jb_sim_get_step_count(JbSim* sim, int32_t* count_dev, void* stream);
+int jb_sim_set_step_count(JbSim* sim, const int32_t* count_dev, void* stream);
+
+/* Parity hook (d->contact after mj_step1 at the current state): per env the number of active contacts, and for up
+ * to `max_con` of them the MuJoCo geom id of the non-floor geom and the signed distance, in ascending geom id.
+ * ncon_dev[num_envs]; geom_dev, dist_dev: [num_envs][max_con]. */
+int jb_sim_get_contacts(JbSim* sim, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream);
+
+/* counters since creation: [0] physics sub-steps, [1] Newton iterations, [2] active contacts summed over sub-steps,
+ * [3] contact-slot overflows, [4] diverged-state resets.  Synchronises the device. */
+int jb_sim_get_counters(JbSim* sim, unsigned long long* out5_host);
+
+int jb_sim_num_envs(const JbSim* sim);
+int jb_sim_obs_stride(const JbSim* sim);
+const char* jb_last_error(void);
+const char* jb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

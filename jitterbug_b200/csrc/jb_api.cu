@@ -1,0 +1,250 @@
+// C-ABI of the batched Jitterbug simulator + the light-weight utility kernels.  See include/jbsim.h for the contract.
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "jb_sim_common.cuh"
+
+static thread_local std::string g_err;
+static int fail(const std::string& msg) { g_err = msg; return 1; }
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+struct JbSim {
+  JbSimConfig cfg;
+  JbDev d;
+  JbModel shared_model;
+  bool per_env;
+  // pinned staging for the host-buffer entry point
+  float *h_act, *h_obs, *h_rew; int32_t* h_st;
+  float *s_act, *s_obs, *s_rew; int32_t* s_st;
+};
+
+static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
+  return s->per_env ? jb_launch_perenv(s->shared_model, s->d, a, st) : jb_launch_shared(s->shared_model, s->d, a, st);
+}
+
+__global__ void jb_heuristic_kernel(const __grid_constant__ JbDev d, const float* __restrict__ obs, float* __restrict__ act) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  float o[JB_OBS_MAX];
+  const float* p = obs + (size_t)e * d.obs_stride;
+#pragma unroll
+  for (int i = 0; i < JB_OBS_MAX; i++) o[i] = i < d.obs_stride ? p[i] : 0.f;
+  act[e] = jb_heuristic<float>(d.task[e], o);
+}
+
+// AoS <-> SoA state transfer (row-major [N][16|15|15] user buffers)
+__global__ void jb_get_state_kernel(const __grid_constant__ JbDev d, float* qpos, float* qvel, float* warm) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int N = d.N;
+  if (qpos) {
+    for (int i = 0; i < 15; i++) qpos[(size_t)e * 16 + i] = d.qpos[i * N + e];
+    qpos[(size_t)e * 16 + 15] = (float)((double)d.qpos[15 * N + e] + 6.28318530717958647692 * (double)d.rev[e]);
+  }
+  if (qvel) for (int i = 0; i < 15; i++) qvel[(size_t)e * 15 + i] = d.qvel[i * N + e];
+  if (warm) for (int i = 0; i < 15; i++) warm[(size_t)e * 15 + i] = d.warm[i * N + e];
+}
+__global__ void jb_set_state_kernel(const __grid_constant__ JbDev d, const float* qpos, const float* qvel, const float* warm) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int N = d.N;
+  if (qpos) {
+    for (int i = 0; i < 15; i++) d.qpos[i * N + e] = qpos[(size_t)e * 16 + i];
+    double qm = qpos[(size_t)e * 16 + 15];
+    double r = ceil((qm - 3.14159265358979323846) / 6.28318530717958647692);
+    d.qpos[15 * N + e] = (float)(qm - 6.28318530717958647692 * r);
+    d.rev[e] = (int)r;
+  }
+  if (qvel) for (int i = 0; i < 15; i++) d.qvel[i * N + e] = qvel[(size_t)e * 15 + i];
+  if (warm) for (int i = 0; i < 15; i++) d.warm[i * N + e] = warm[(size_t)e * 15 + i];
+}
+__global__ void jb_target_kernel(const __grid_constant__ JbDev d, float* tgt, int set) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  for (int i = 0; i < 4; i++) {
+    if (set) d.target[i * d.N + e] = tgt[(size_t)e * 4 + i];
+    else tgt[(size_t)e * 4 + i] = d.target[i * d.N + e];
+  }
+}
+__global__ void jb_count_kernel(const __grid_constant__ JbDev d, int* cnt, int set) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  if (set) { d.step_count[e] = cnt[e]; d.reset_next[e] = 0; }
+  else cnt[e] = d.step_count[e];
+}
+
+// ------------------------------------------------------------------------------------------------ C-ABI
+extern "C" {
+
+const char* jb_last_error(void) { return g_err.c_str(); }
+const char* jb_version(void) { return "jbsim 0.1 (sm_100a, thread-per-env)"; }
+int jb_sim_num_envs(const JbSim* sim) { return sim ? sim->cfg.num_envs : 0; }
+int jb_sim_obs_stride(const JbSim* sim) { return sim ? sim->cfg.obs_stride : 0; }
+
+static int grid_of(int n) { return (n + JB_BLOCK - 1) / JB_BLOCK; }
+
+int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models, const int32_t* task_ids_host) {
+  if (!out || !cfg || !models_host) return fail("jb_sim_create: null argument");
+  if (cfg->num_envs <= 0) return fail("jb_sim_create: num_envs must be positive");
+  if (n_models != 1 && n_models != cfg->num_envs) return fail("jb_sim_create: n_models must be 1 or num_envs");
+  if (cfg->obs_stride < 15 || cfg->obs_stride > JB_OBS_MAX) return fail("jb_sim_create: obs_stride must be in [15, 19]");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail("jb_sim_create: no CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  JbSim* s = new JbSim();
+  memset(s, 0, sizeof(*s));
+  s->cfg = *cfg;
+  s->shared_model = models_host[0];
+  s->per_env = n_models != 1;
+  const size_t N = cfg->num_envs;
+  JbDev& d = s->d;
+  d.N = (int)N; d.n_sub = cfg->n_sub_steps; d.step_limit = cfg->step_limit; d.random_pose = cfg->random_pose;
+  d.obs_stride = cfg->obs_stride; d.seed = cfg->seed; d.env_id_offset = cfg->env_id_offset;
+  CUDA_TRY(cudaMalloc(&d.qpos, 16 * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d.qvel, 15 * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d.warm, 15 * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d.target, 4 * N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&d.rev, N * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d.task, N * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d.step_count, N * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d.episode, N * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&d.reset_next, N));
+  CUDA_TRY(cudaMalloc(&d.counters, 5 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d.qpos, 0, 16 * N * sizeof(float)));
+  CUDA_TRY(cudaMemset(d.qvel, 0, 15 * N * sizeof(float)));
+  CUDA_TRY(cudaMemset(d.warm, 0, 15 * N * sizeof(float)));
+  CUDA_TRY(cudaMemset(d.target, 0, 4 * N * sizeof(float)));
+  CUDA_TRY(cudaMemset(d.rev, 0, N * sizeof(int)));
+  CUDA_TRY(cudaMemset(d.step_count, 0, N * sizeof(int)));
+  CUDA_TRY(cudaMemset(d.episode, 0, N * sizeof(int)));
+  CUDA_TRY(cudaMemset(d.reset_next, 1, N));           // a step() before any reset() is a reset (dm_control)
+  CUDA_TRY(cudaMemset(d.counters, 0, 5 * sizeof(unsigned long long)));
+  if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
+  else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
+  if (s->per_env) {
+    JbModel* mdev = nullptr;
+    CUDA_TRY(cudaMalloc(&mdev, N * sizeof(JbModel)));
+    CUDA_TRY(cudaMemcpy(mdev, models_host, N * sizeof(JbModel), cudaMemcpyHostToDevice));
+    d.models = mdev;
+  }
+  CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_st, N * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&s->s_act, N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&s->s_obs, N * cfg->obs_stride * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&s->s_rew, N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&s->s_st, N * sizeof(int32_t)));
+  *out = s;
+  return 0;
+}
+
+void jb_sim_destroy(JbSim* s) {
+  if (!s) return;
+  cudaSetDevice(s->cfg.device);
+  JbDev& d = s->d;
+  cudaFree(d.qpos); cudaFree(d.qvel); cudaFree(d.warm); cudaFree(d.target); cudaFree(d.rev); cudaFree(d.task);
+  cudaFree(d.step_count); cudaFree(d.episode); cudaFree(d.reset_next); cudaFree(d.counters);
+  if (d.models) cudaFree((void*)d.models);
+  cudaFreeHost(s->h_act); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_rew); cudaFreeHost(s->h_st);
+  cudaFree(s->s_act); cudaFree(s->s_obs); cudaFree(s->s_rew); cudaFree(s->s_st);
+  delete s;
+}
+
+int jb_sim_reset(JbSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!s) return fail("jb_sim_reset: null sim");
+  cudaStream_t st = (cudaStream_t)stream;
+  JbLaunchArgs a = {JB_MODE_RESET, mask_dev, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  CUDA_TRY(launch(s, a, st));
+  return 0;
+}
+
+int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* reward_dev, int32_t* step_type_dev, void* stream) {
+  if (!s || !actions_dev) return fail("jb_sim_step: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr, nullptr, 0};
+  CUDA_TRY(launch(s, a, st));
+  return 0;
+}
+
+int jb_sim_step_host(JbSim* s, const float* actions_host, float* obs_host, float* reward_host, int32_t* step_type_host, void* stream) {
+  if (!s || !actions_host) return fail("jb_sim_step_host: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = s->d.N, os = s->cfg.obs_stride;
+  memcpy(s->h_act, actions_host, N * sizeof(float));
+  CUDA_TRY(cudaMemcpyAsync(s->s_act, s->h_act, N * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (jb_sim_step(s, s->s_act, s->s_obs, s->s_rew, s->s_st, stream)) return 1;
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(s->h_obs, s->s_obs, N * os * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (step_type_host) CUDA_TRY(cudaMemcpyAsync(s->h_st, s->s_st, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (obs_host) memcpy(obs_host, s->h_obs, N * os * sizeof(float));
+  if (reward_host) memcpy(reward_host, s->h_rew, N * sizeof(float));
+  if (step_type_host) memcpy(step_type_host, s->h_st, N * sizeof(int32_t));
+  return 0;
+}
+
+int jb_sim_heuristic_actions(JbSim* s, const float* obs_dev, float* actions_dev, void* stream) {
+  if (!s || !obs_dev || !actions_dev) return fail("jb_sim_heuristic_actions: null argument");
+  jb_heuristic_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, obs_dev, actions_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int jb_sim_get_state(JbSim* s, float* qpos_dev, float* qvel_dev, float* warm_dev, void* stream) {
+  if (!s) return fail("jb_sim_get_state: null sim");
+  jb_get_state_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, qpos_dev, qvel_dev, warm_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_set_state(JbSim* s, const float* qpos_dev, const float* qvel_dev, const float* warm_dev, void* stream) {
+  if (!s) return fail("jb_sim_set_state: null sim");
+  jb_set_state_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, qpos_dev, qvel_dev, warm_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_get_target(JbSim* s, float* target_dev, void* stream) {
+  if (!s || !target_dev) return fail("jb_sim_get_target: null argument");
+  jb_target_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, target_dev, 0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_set_target(JbSim* s, const float* target_dev, void* stream) {
+  if (!s || !target_dev) return fail("jb_sim_set_target: null argument");
+  jb_target_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, (float*)target_dev, 1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_get_step_count(JbSim* s, int32_t* count_dev, void* stream) {
+  if (!s || !count_dev) return fail("jb_sim_get_step_count: null argument");
+  jb_count_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, count_dev, 0);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_set_step_count(JbSim* s, const int32_t* count_dev, void* stream) {
+  if (!s || !count_dev) return fail("jb_sim_set_step_count: null argument");
+  jb_count_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, (int*)count_dev, 1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream) {
+  if (!s || !ncon_dev || !geom_dev || !dist_dev || max_con <= 0) return fail("jb_sim_get_contacts: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  JbLaunchArgs a = {JB_MODE_CONTACTS, nullptr, nullptr, nullptr, nullptr, nullptr, ncon_dev, geom_dev, dist_dev, max_con};
+  CUDA_TRY(launch(s, a, st));
+  return 0;
+}
+int jb_sim_get_counters(JbSim* s, unsigned long long* out5_host) {
+  if (!s || !out5_host) return fail("jb_sim_get_counters: null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out5_host, s->d.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

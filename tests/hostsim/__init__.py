@@ -1,0 +1,55 @@
+"""TEST-ONLY ctypes wrapper of tests/hostsim/hostsim.cpp (host build of the GPU sub-step algorithm)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from jitterbug_b200 import model as jbmodel
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libhostsim.so")
+_SRC = [os.path.join(_HERE, "hostsim.cpp"),
+        os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", "jb_dynamics.cuh"),
+        os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", "jb_model.h")]
+
+
+def _diag_struct(real):
+    class Diag(C.Structure):
+        _fields_ = [("M", (real * 15) * 15), ("bias", real * 15), ("fsmooth", real * 15), ("asmooth", real * 15),
+                    ("qacc", real * 15), ("fcon", real * 15), ("Rw", real * 9),
+                    ("ncon", C.c_int), ("geom", C.c_int * 64), ("dist", real * 64), ("cpos", (real * 3) * 64),
+                    ("newton_iters", C.c_int), ("overflow", C.c_int)]
+    return Diag
+
+
+DiagD, DiagF = _diag_struct(C.c_double), _diag_struct(C.c_float)
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in _SRC):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++14", "-ffp-contract=off",
+                                   "-o", _SO, _SRC[0]])
+        _lib = C.CDLL(_SO)
+        assert _lib.hs_sizeof_model_f32() == C.sizeof(jbmodel.JbModelF)
+        assert _lib.hs_sizeof_model_f64() == C.sizeof(jbmodel.JbModelD)
+        assert _lib.hs_sizeof_diag_f64() == C.sizeof(DiagD), (_lib.hs_sizeof_diag_f64(), C.sizeof(DiagD))
+        assert _lib.hs_sizeof_diag_f32() == C.sizeof(DiagF)
+    return _lib
+
+
+def substeps(model_struct, qpos, qvel, warm, ctrl, nsub=1, double=True, want_diag=False):
+    """Advance one env by ``nsub`` sub-steps with the host build.  Returns (qpos, qvel, warm, iters, diag)."""
+    L = lib()
+    dt = np.float64 if double else np.float32
+    real = C.c_double if double else C.c_float
+    q = np.array(qpos, dtype=dt).copy(); v = np.array(qvel, dtype=dt).copy(); w = np.array(warm, dtype=dt).copy()
+    diag = (DiagD if double else DiagF)() if want_diag else None
+    fn = L.hs_substeps_f64 if double else L.hs_substeps_f32
+    fn.restype = C.c_int
+    it = fn(C.byref(model_struct), q.ctypes.data_as(C.POINTER(real)), v.ctypes.data_as(C.POINTER(real)),
+            w.ctypes.data_as(C.POINTER(real)), real(ctrl), C.c_int(nsub), C.byref(diag) if want_diag else None)
+    return q, v, w, it, diag
