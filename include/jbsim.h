@@ -83,6 +83,10 @@ int jb_sim_get_contacts(JbSim* sim, int32_t* ncon_dev, int32_t* geom_dev, float*
  * [3] contact-slot overflows, [4] diverged-state resets.  Synchronises the device. */
 int jb_sim_get_counters(JbSim* sim, unsigned long long* out5_host);
 
+/* FP32 FMA-pipe peak of `device` in TFLOP/s (FFMA-chain microbenchmark): the roofline denominator of this
+ * compute-bound path.  Synchronises the device. */
+int jb_measure_fp32_peak(int device, double* tflops_out);
+
 int jb_sim_num_envs(const JbSim* sim);
 int jb_sim_obs_stride(const JbSim* sim);
 const char* jb_last_error(void);

@@ -78,6 +78,22 @@ __global__ void jb_count_kernel(const __grid_constant__ JbDev d, int* cnt, int s
   else cnt[e] = d.step_count[e];
 }
 
+// FP32 FMA-pipe peak: 16 independent FFMA chains per thread, enough CTAs to fill the chip (roofline denominator
+// for this compute-bound path; MEASURED_PEAKS.json only carries HBM and tensor numbers).
+__global__ void jb_fma_peak_kernel(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += x[i];
+  if (s == 12345.678f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // never true; keeps the chains alive
+}
+
 // ------------------------------------------------------------------------------------------------ C-ABI
 extern "C" {
 
@@ -244,6 +260,32 @@ int jb_sim_get_counters(JbSim* s, unsigned long long* out5_host) {
   if (!s || !out5_host) return fail("jb_sim_get_counters: null argument");
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out5_host, s->d.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int jb_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return fail("jb_measure_fp32_peak: null argument");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  float* buf = nullptr;
+  CUDA_TRY(cudaMalloc(&buf, (size_t)threads * blocks * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CUDA_TRY(cudaEventRecord(e0));
+    jb_fma_peak_kernel<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 16.0 * (double)iters * threads * blocks / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+  *tflops_out = best;
   return 0;
 }
 
