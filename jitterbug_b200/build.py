@@ -1,7 +1,6 @@
 """Builds ``jitterbug_b200/_lib/libjbsim.so`` (CUDA, sm_100a) in-tree with nvcc.
 
-Three translation units: the two heavy instantiations of the fused step kernel (shared model / per-env models) and
-the C-ABI + utility kernels; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
+Two translation units: the fused quad-per-env step kernel and the C-ABI + utility kernels; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
 """
 
 from __future__ import annotations
@@ -16,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
-UNITS = ["jb_kernel_shared.cu", "jb_kernel_perenv.cu", "jb_api.cu"]
+UNITS = ["jb_sim_kernel.cu", "jb_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

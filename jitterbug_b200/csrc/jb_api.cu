@@ -4,6 +4,8 @@
 #include <string>
 
 #include "jb_sim_common.cuh"
+#include "jb_task.cuh"
+#include <vector>
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) { g_err = msg; return 1; }
@@ -16,15 +18,38 @@ static int fail(const std::string& msg) { g_err = msg; return 1; }
 struct JbSim {
   JbSimConfig cfg;
   JbDev d;
-  JbModel shared_model;
   bool per_env;
+  int* rep_geom; float* rep_dist;   // contact-report staging [N][4*JBQ_CAP], allocated on first use
   // pinned staging for the host-buffer entry point
   float *h_act, *h_obs, *h_rew; int32_t* h_st;
   float *s_act, *s_obs, *s_rew; int32_t* s_st;
 };
 
-static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
-  return s->per_env ? jb_launch_perenv(s->shared_model, s->d, a, st) : jb_launch_shared(s->shared_model, s->d, a, st);
+static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) { return jb_launch_sim(s->d, a, st); }
+
+#define JB_REP (4 * 8)   /* 4 lanes x JBQ_CAP staging slots per env */
+
+// staging [N][32] (-1 = empty) -> compact lists in ascending MuJoCo geom id
+__global__ void jb_compact_contacts_kernel(int N, const int* rep_geom, const float* rep_dist, int* ncon, int* geom,
+                                           float* dist, int max_con) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  int gl[JB_REP]; float dl[JB_REP];
+  int n = 0;
+  for (int i = 0; i < JB_REP; i++) {
+    int gg = rep_geom[(size_t)e * JB_REP + i];
+    if (gg < 0) continue;
+    float dd = rep_dist[(size_t)e * JB_REP + i];
+    int j = n - 1;
+    while (j >= 0 && gl[j] > gg) { gl[j + 1] = gl[j]; dl[j + 1] = dl[j]; j--; }
+    gl[j + 1] = gg; dl[j + 1] = dd;
+    n++;
+  }
+  ncon[e] = n;
+  for (int i = 0; i < max_con; i++) {
+    geom[(size_t)e * max_con + i] = i < n ? gl[i] : -1;
+    dist[(size_t)e * max_con + i] = i < n ? dl[i] : 0.f;
+  }
 }
 
 __global__ void jb_heuristic_kernel(const __grid_constant__ JbDev d, const float* __restrict__ obs, float* __restrict__ act) {
@@ -98,7 +123,7 @@ __global__ void jb_fma_peak_kernel(float* out, int iters, float a, float b) {
 extern "C" {
 
 const char* jb_last_error(void) { return g_err.c_str(); }
-const char* jb_version(void) { return "jbsim 0.1 (sm_100a, thread-per-env)"; }
+const char* jb_version(void) { return "jbsim 0.2 (sm_100a, quad-per-env)"; }
 int jb_sim_num_envs(const JbSim* sim) { return sim ? sim->cfg.num_envs : 0; }
 int jb_sim_obs_stride(const JbSim* sim) { return sim ? sim->cfg.obs_stride : 0; }
 
@@ -116,7 +141,6 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   JbSim* s = new JbSim();
   memset(s, 0, sizeof(*s));
   s->cfg = *cfg;
-  s->shared_model = models_host[0];
   s->per_env = n_models != 1;
   const size_t N = cfg->num_envs;
   JbDev& d = s->d;
@@ -143,11 +167,17 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   CUDA_TRY(cudaMemset(d.counters, 0, 5 * sizeof(unsigned long long)));
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
-  if (s->per_env) {
-    JbModel* mdev = nullptr;
-    CUDA_TRY(cudaMalloc(&mdev, N * sizeof(JbModel)));
-    CUDA_TRY(cudaMemcpy(mdev, models_host, N * sizeof(JbModel), cudaMemcpyHostToDevice));
-    d.models = mdev;
+  {
+    // pack the model(s) into the lane-interleaved float layout the quad kernel stages in shared memory
+    const size_t nm = (size_t)n_models;
+    std::vector<float> packed(nm * JBP_SIZE);
+    for (size_t i = 0; i < nm; i++) jb_pack_model<float, JbModel>(models_host[i], packed.data() + i * JBP_SIZE);
+    float* pdev = nullptr;
+    CUDA_TRY(cudaMalloc(&pdev, packed.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(pdev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    d.packed = pdev;
+    d.per_env = s->per_env ? 1 : 0;
+    CUDA_TRY(jb_configure_kernels());
   }
   CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
@@ -167,7 +197,9 @@ void jb_sim_destroy(JbSim* s) {
   JbDev& d = s->d;
   cudaFree(d.qpos); cudaFree(d.qvel); cudaFree(d.warm); cudaFree(d.target); cudaFree(d.rev); cudaFree(d.task);
   cudaFree(d.step_count); cudaFree(d.episode); cudaFree(d.reset_next); cudaFree(d.counters);
-  if (d.models) cudaFree((void*)d.models);
+  if (d.packed) cudaFree((void*)d.packed);
+  if (s->rep_geom) cudaFree(s->rep_geom);
+  if (s->rep_dist) cudaFree(s->rep_dist);
   cudaFreeHost(s->h_act); cudaFreeHost(s->h_obs); cudaFreeHost(s->h_rew); cudaFreeHost(s->h_st);
   cudaFree(s->s_act); cudaFree(s->s_obs); cudaFree(s->s_rew); cudaFree(s->s_st);
   delete s;
@@ -176,7 +208,7 @@ void jb_sim_destroy(JbSim* s) {
 int jb_sim_reset(JbSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!s) return fail("jb_sim_reset: null sim");
   cudaStream_t st = (cudaStream_t)stream;
-  JbLaunchArgs a = {JB_MODE_RESET, mask_dev, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  JbLaunchArgs a = {JB_MODE_RESET, mask_dev, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr};
   CUDA_TRY(launch(s, a, st));
   return 0;
 }
@@ -184,7 +216,7 @@ int jb_sim_reset(JbSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream
 int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* reward_dev, int32_t* step_type_dev, void* stream) {
   if (!s || !actions_dev) return fail("jb_sim_step: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr, nullptr, 0};
+  JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr};
   CUDA_TRY(launch(s, a, st));
   return 0;
 }
@@ -252,8 +284,15 @@ int jb_sim_set_step_count(JbSim* s, const int32_t* count_dev, void* stream) {
 int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream) {
   if (!s || !ncon_dev || !geom_dev || !dist_dev || max_con <= 0) return fail("jb_sim_get_contacts: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
-  JbLaunchArgs a = {JB_MODE_CONTACTS, nullptr, nullptr, nullptr, nullptr, nullptr, ncon_dev, geom_dev, dist_dev, max_con};
+  if (!s->rep_geom) {
+    CUDA_TRY(cudaMalloc(&s->rep_geom, (size_t)s->d.N * JB_REP * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&s->rep_dist, (size_t)s->d.N * JB_REP * sizeof(float)));
+  }
+  JbLaunchArgs a = {JB_MODE_CONTACTS, nullptr, nullptr, nullptr, nullptr, nullptr, s->rep_geom, s->rep_dist};
   CUDA_TRY(launch(s, a, st));
+  jb_compact_contacts_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, st>>>(s->d.N, s->rep_geom, s->rep_dist, ncon_dev, geom_dev,
+                                                                    dist_dev, max_con);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_get_counters(JbSim* s, unsigned long long* out5_host) {

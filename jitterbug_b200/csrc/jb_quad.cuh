@@ -1,0 +1,912 @@
+// The physics sub-step for ONE Jitterbug executed by a QUAD of 4 cooperating lanes (lane l owns leg l).
+//
+// Same mathematics as documented in DESIGN.md section 3 (MuJoCo's mj_step2 ; mj_step1 restated in the root body's
+// frame, product-of-exponentials kinematics, arrow-structured L'DL, primal Newton with exact line search), but
+// written SPMD: every lane runs this code; data that belongs to one leg (joint state, the 2x2 inertia block and its
+// coupling to the root, that leg's contacts) lives only in that leg's lane, data of the root / rotor is replicated in
+// all four lanes, and the few sums over legs go through `Comm::sum*` (two __shfl_xor_sync steps on the GPU, a fiber
+// rendezvous in the test-only host build).  Butterfly sums are bitwise identical in the 4 lanes, so replicated
+// control flow (Newton iterations, line search) never diverges inside a quad.
+//
+// Why a quad and not a thread per env: the thread-per-env version (profiles/r01_v1_*) needed ~MBs of unrolled SASS,
+// 255 registers + 4 KB of stack and diverged 32 ways per warp; it stalled ~90% on instruction fetch.  With one leg per
+// lane the per-lane working set fits in registers, the code is 4x smaller, and a warp holds 8 envs.
+#ifndef JB_QUAD_CUH
+#define JB_QUAD_CUH
+
+#include "jb_math.cuh"
+#include "jb_packed.h"
+#include <stdint.h>
+
+#define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms) */
+#define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+template <typename T> struct QState {
+  T pos[3], quat[4], vlin[3], w[3];     // root: replicated in the 4 lanes (MuJoCo coordinates: world linear, body angular)
+  T qa, qb, va, vb;                     // this lane's leg: hinge 1 / hinge 2 angle and velocity
+  T qm, vm; int rev;                    // motor: replicated; qpos[15] = qm + 2*pi*rev
+  T wr[6], wla, wlb, wmo;               // qacc_warmstart, same split
+};
+template <typename T> struct QVec { T r[6]; T la, lb, mo; };
+template <typename T> struct QArrow {   // R, cm, mm replicated; aa..cb this lane's leg
+  T R[21]; T cm[6], mm; T aa, ab, bb, ca[6], cb[6];
+};
+enum { QK_LEG = 0, QK_ROOT = 1, QK_ROTOR = 2 };
+template <typename T> struct QCon {
+  T x[3], D, ar0, uref[3];              // point (root comps), 1/Rpy, -K*imp*dist, -B*v_point (WORLD comps)
+  T ww[3], jv[3];                       // solver scratch (WORLD comps): J a - uref ; J search
+  T ja[3], jb[3];                       // joint Jacobian columns (root comps): leg hinge 1 / 2, or motor in ja
+  int kind;
+};
+template <typename T> struct QConSet { QCon<T> c[JBQ_CAP]; int n, overflow; };
+template <typename T> struct QReport { int* geom; T* dist; int stride; };     // parity hook: [lane*JBQ_CAP + i]
+
+template <typename T> JB_HD void qv_zero(QVec<T>& v) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) v.r[i] = 0;
+  v.la = 0; v.lb = 0; v.mo = 0;
+}
+template <typename T> JB_HD void qv_axpy(QVec<T>& y, T a, const QVec<T>& x) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) y.r[i] += a * x.r[i];
+  y.la += a * x.la; y.lb += a * x.lb; y.mo += a * x.mo;
+}
+// replicated part of a dot product (root + motor); the leg part must be quad-summed by the caller
+template <typename T> JB_HD T qv_dot_rep(const QVec<T>& a, const QVec<T>& b) {
+  T s = a.mo * b.mo;
+#pragma unroll
+  for (int i = 0; i < 6; i++) s += a.r[i] * b.r[i];
+  return s;
+}
+template <typename T> JB_HD T qv_dot_leg(const QVec<T>& a, const QVec<T>& b) { return a.la * b.la + a.lb * b.lb; }
+
+// y = A x
+template <typename T, typename Comm> JB_HD void qarrow_mul(Comm& cm, QVec<T>& y, const QArrow<T>& A, const QVec<T>& x) {
+  T p[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) p[i] = A.ca[i] * x.la + A.cb[i] * x.lb;
+  cm.sumN(p, 6);
+  T sa = A.aa * x.la + A.ab * x.lb, sb = A.ab * x.la + A.bb * x.lb, sm = A.mm * x.mo;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    T s = p[i] + A.cm[i] * x.mo;
+#pragma unroll
+    for (int j = 0; j < 6; j++) s += A.R[i >= j ? JBQ_TRI(i, j) : JBQ_TRI(j, i)] * x.r[j];
+    y.r[i] = s;
+    sa += A.ca[i] * x.r[i]; sb += A.cb[i] * x.r[i]; sm += A.cm[i] * x.r[i];
+  }
+  y.la = sa; y.lb = sb; y.mo = sm;
+}
+
+// Leaf-first L'DL (MuJoCo's elimination order).  `part` (28 values or nullptr) carries this lane's additive
+// contributions to the replicated block: R[21], cm[6], mm -- the Newton Hessian's contact terms.
+template <typename T, typename Comm> JB_HD void qarrow_factor(Comm& cm, QArrow<T>& A, const T* part) {
+  T red[28];
+  T ibb = (T)1 / A.bb;
+  T lab = A.ab * ibb;
+  T Lb[6], La[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) Lb[i] = A.cb[i] * ibb;
+  A.aa -= lab * A.ab;
+#pragma unroll
+  for (int i = 0; i < 6; i++) A.ca[i] -= lab * A.cb[i];
+  T iaa = (T)1 / A.aa;
+#pragma unroll
+  for (int i = 0; i < 6; i++) La[i] = A.ca[i] * iaa;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) red[JBQ_TRI(i, j)] = (part ? part[JBQ_TRI(i, j)] : (T)0) - Lb[i] * A.cb[j] - La[i] * A.ca[j];
+  if (part) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) red[21 + i] = part[21 + i];
+    cm.sumN(red, 28);
+#pragma unroll
+    for (int i = 0; i < 6; i++) A.cm[i] += red[21 + i];
+    A.mm += red[27];
+  } else {
+    cm.sumN(red, 21);
+  }
+#pragma unroll
+  for (int i = 0; i < 21; i++) A.R[i] += red[i];
+  A.bb = ibb; A.ab = lab; A.aa = iaa;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { A.cb[i] = Lb[i]; A.ca[i] = La[i]; }
+  // motor dof (replicated)
+  T imm = (T)1 / A.mm;
+  T Lm[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) Lm[i] = A.cm[i] * imm;
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j <= i; j++) A.R[JBQ_TRI(i, j)] -= Lm[i] * A.cm[j];
+  A.mm = imm;
+#pragma unroll
+  for (int i = 0; i < 6; i++) A.cm[i] = Lm[i];
+  // dense LDL' of the 6x6 Schur complement (unit L below the diagonal, reciprocal pivots on it), replicated
+  T dv[6];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    T d = A.R[JBQ_TRI(j, j)];
+    T ld[6];
+#pragma unroll
+    for (int k = 0; k < j; k++) { ld[k] = A.R[JBQ_TRI(j, k)] * dv[k]; d -= A.R[JBQ_TRI(j, k)] * ld[k]; }
+    dv[j] = d;
+    T id = (T)1 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      T s = A.R[JBQ_TRI(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) s -= A.R[JBQ_TRI(i, k)] * ld[k];
+      A.R[JBQ_TRI(i, j)] = s * id;
+    }
+    A.R[JBQ_TRI(j, j)] = id;
+  }
+}
+
+template <typename T, typename Comm> JB_HD void qarrow_solve(Comm& cm, QVec<T>& x, const QArrow<T>& F, const QVec<T>& r) {
+  T ra = r.la - F.ab * r.lb;
+  T rr[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) rr[i] = -(F.cb[i] * r.lb + F.ca[i] * ra);
+  cm.sumN(rr, 6);
+#pragma unroll
+  for (int i = 0; i < 6; i++) rr[i] += r.r[i] - F.cm[i] * r.mo;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+#pragma unroll
+    for (int k = 0; k < i; k++) rr[i] -= F.R[JBQ_TRI(i, k)] * rr[k];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) rr[i] *= F.R[JBQ_TRI(i, i)];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) rr[i] -= F.R[JBQ_TRI(k, i)] * rr[k];
+  }
+  T xa = ra * F.aa, xb = r.lb * F.bb, xm = r.mo * F.mm;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { x.r[i] = rr[i]; xa -= F.ca[i] * rr[i]; xb -= F.cb[i] * rr[i]; xm -= F.cm[i] * rr[i]; }
+  xb -= F.ab * xa;
+  x.la = xa; x.lb = xb; x.mo = xm;
+}
+
+// ------------------------------------------------------------------------------------------------ contacts
+// MuJoCo's solimp sigmoid (getimpedance), impedance only; si = packed solimp[5]
+template <typename T> JB_HD T jbq_impedance(const T* si, T dist) {
+  T d0 = jb_min((T)0.9999, jb_max((T)0.0001, si[0])), d1 = jb_min((T)0.9999, jb_max((T)0.0001, si[1]));
+  T width = si[2], mid = jb_min((T)0.9999, jb_max((T)0.0001, si[3])), power = si[4];
+  if (d0 == d1 || width <= (T)1e-15) return (T)0.5 * (d0 + d1);
+  T x = jb_abs(dist) / width;
+  if (x >= (T)1) return d1;
+  if (x <= (T)0) return d0;
+  T y;
+  if (power == (T)2) y = x <= mid ? x * x / mid : (T)1 - ((T)1 - x) * ((T)1 - x) / ((T)1 - mid);
+  else if (power <= (T)1) y = x;
+  else {
+#if defined(__CUDA_ARCH__)
+    y = x <= mid ? (T)(powf((float)x, (float)power) / powf((float)mid, (float)power - 1.f))
+                 : (T)(1.f - powf(1.f - (float)x, (float)power) / powf(1.f - (float)mid, (float)power - 1.f));
+#else
+    y = x <= mid ? (T)(pow((double)x, (double)power) / pow((double)mid, (double)power - 1))
+                 : (T)(1 - pow(1 - (double)x, (double)power) / pow(1 - (double)mid, (double)power - 1));
+#endif
+  }
+  return d0 + y * (d1 - d0);
+}
+
+template <typename T> struct QFrame {    // per-substep root-frame quantities (replicated)
+  T Rw[9], n[3], pz, vr[3], w[3];
+};
+template <typename T> struct QBody {     // how a geom's body moves: joint columns for a point x
+  int kind;                              // QK_*
+  const T* a1; const T* p1; T qd1;       // first joint above the body (leg hinge 1, or the motor)
+  const T* a2; const T* p2; T qd2; bool lower;
+  T invw;
+};
+
+template <typename T>
+JB_HD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
+                    const QReport<T>* rep, int lane) {
+  if (!(dist < (T)0)) return;            // dist >= includemargin (= 0): MuJoCo excludes it from the solver
+  int i = cs.n;
+  if (i >= JBQ_CAP) { cs.overflow = 1; return; }
+  cs.n = i + 1;
+  QCon<T>& c = cs.c[i];
+  c.x[0] = x[0]; c.x[1] = x[1]; c.x[2] = x[2];
+  c.kind = b.kind;
+  T v[3], t[3], r[3];
+  cross3(t, fr.w, x);
+  v[0] = fr.vr[0] + t[0]; v[1] = fr.vr[1] + t[1]; v[2] = fr.vr[2] + t[2];
+  c.ja[0] = c.ja[1] = c.ja[2] = (T)0; c.jb[0] = c.jb[1] = c.jb[2] = (T)0;
+  if (b.kind != QK_ROOT) {
+    sub3(r, x, b.p1); cross3(c.ja, b.a1, r); addscl3(v, c.ja, b.qd1);
+    if (b.lower) { sub3(r, x, b.p2); cross3(c.jb, b.a2, r); addscl3(v, c.jb, b.qd2); }
+  }
+  T imp = jbq_impedance<T>(g + G_SOLIMP, dist);
+  T mu = g[G_FRIC];
+  // diagApprox = tran*(1+mu^2); R0 = (1-imp)/imp*diagApprox; Rpy = 2*mu_reg^2*R0, mu_reg = mu/sqrt(impratio)
+  T Rpy = (T)2 * mu * mu / g[G_IMPRATIO] * ((T)1 - imp) / imp * b.invw * ((T)1 + mu * mu);
+  c.D = (T)1 / jb_max(Rpy, (T)1e-15);
+  c.ar0 = -g[G_SOLK] * imp * dist;
+  T vw[3];
+  mulMV(vw, fr.Rw, v);
+  c.uref[0] = -g[G_SOLB] * vw[0]; c.uref[1] = -g[G_SOLB] * vw[1]; c.uref[2] = -g[G_SOLB] * vw[2];
+  if (rep) { rep->geom[(lane * JBQ_CAP + i) * rep->stride] = geom; rep->dist[(lane * JBQ_CAP + i) * rep->stride] = dist; }
+}
+
+#define JBQ_EMIT(geom, x, dist) jbq_emit<T>(g, cs, fr, b, (geom), (x), (dist), rep, lane)
+
+template <typename T>
+JB_HD void jbq_col_sphere(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c, T r,
+                          const QReport<T>* rep, int lane) {
+  T dist = fr.pz + dot3(fr.n, c) - r;
+  if (dist > (T)0) return;
+  T s = r + (T)0.5 * dist;
+  T x[3] = {c[0] - fr.n[0] * s, c[1] - fr.n[1] * s, c[2] - fr.n[2] * s};
+  JBQ_EMIT(geom, x, dist);
+}
+
+// mjc_PlaneCylinder; xax is only needed when the axis is exactly parallel to the floor normal
+template <typename T>
+JB_HD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+                            const T* ax_in, const T* xax, T r, T hl, const QReport<T>* rep, int lane) {
+  T dist0 = fr.pz + dot3(fr.n, c);
+  T ax[3] = {ax_in[0], ax_in[1], ax_in[2]};
+  T prjaxis = dot3(fr.n, ax);
+  if (prjaxis > (T)0) { ax[0] = -ax[0]; ax[1] = -ax[1]; ax[2] = -ax[2]; prjaxis = -prjaxis; }
+  T vec[3] = {ax[0] * prjaxis - fr.n[0], ax[1] * prjaxis - fr.n[1], ax[2] * prjaxis - fr.n[2]};
+  T len_sqr = dot3(vec, vec);
+  if (len_sqr >= (T)1e-30) {
+    T s = r / jb_sqrt(len_sqr);
+    vec[0] *= s; vec[1] *= s; vec[2] *= s;
+  } else {
+    vec[0] = xax[0] * r; vec[1] = xax[1] * r; vec[2] = xax[2] * r;
+  }
+  T prjvec = dot3(vec, fr.n);
+  ax[0] *= hl; ax[1] *= hl; ax[2] *= hl;
+  prjaxis *= hl;
+  T d1 = dist0 + prjaxis + prjvec;
+  if (d1 > (T)0) return;
+  T x[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] + ax[k] - fr.n[k] * d1 * (T)0.5;
+  JBQ_EMIT(geom, x, d1);
+  T d2 = dist0 - prjaxis + prjvec;
+  if (d2 <= (T)0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] - ax[k] - fr.n[k] * d2 * (T)0.5;
+    JBQ_EMIT(geom, x, d2);
+  }
+  T d3 = dist0 + prjaxis - prjvec * (T)0.5;
+  if (d3 <= (T)0) {
+    T v1[3];
+    cross3(v1, vec, ax);
+    T nn = jb_sqrt(dot3(v1, v1));
+    if (nn < (T)1e-15) { v1[0] = 1; v1[1] = 0; v1[2] = 0; nn = 1; }
+    T s = r * (T)0.8660254037844386 / nn;
+    v1[0] *= s; v1[1] *= s; v1[2] *= s;
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = c[k] + v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
+    JBQ_EMIT(geom, x, d3);
+#pragma unroll
+    for (int k = 0; k < 3; k++) x[k] = c[k] - v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
+    JBQ_EMIT(geom, x, d3);
+  }
+}
+
+template <typename T>
+JB_HD void jbq_col_box(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c, const T* Rg,
+                       const T* half, const QReport<T>* rep, int lane) {
+  T dist = fr.pz + dot3(fr.n, c);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    T v[3] = {(i & 1) ? half[0] : -half[0], (i & 2) ? half[1] : -half[1], (i & 4) ? half[2] : -half[2]};
+    T corner[3];
+    mulMV(corner, Rg, v);
+    T ldist = dot3(fr.n, corner);
+    if (dist + ldist > (T)0 || ldist > (T)0) continue;
+    T cd = dist + ldist;
+    T x[3] = {corner[0] + c[0] - fr.n[0] * cd * (T)0.5, corner[1] + c[1] - fr.n[1] * cd * (T)0.5,
+              corner[2] + c[2] - fr.n[2] * cd * (T)0.5};
+    JBQ_EMIT(geom, x, cd);
+    if (++cnt >= 4) return;
+  }
+}
+
+template <typename T>
+JB_HD void jbq_col_ellipsoid(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+                             const T* Rg, const T* size, const QReport<T>* rep, int lane) {
+  T dir[3] = {-fr.n[0], -fr.n[1], -fr.n[2]}, loc[3];
+  mulMTV(loc, Rg, dir);
+  loc[0] *= size[0]; loc[1] *= size[1]; loc[2] *= size[2];
+  T nrm = jb_sqrt(dot3(loc, loc));
+  if (nrm < (T)1e-15) nrm = (T)1e-15;
+  loc[0] = loc[0] / nrm * size[0]; loc[1] = loc[1] / nrm * size[1]; loc[2] = loc[2] / nrm * size[2];
+  T wv[3], sup[3];
+  mulMV(wv, Rg, loc);
+  add3(sup, wv, c);
+  T dist = fr.pz + dot3(fr.n, sup);
+  if (dist > (T)0) return;
+  T x[3] = {sup[0] - fr.n[0] * (T)0.5 * dist, sup[1] - fr.n[1] * (T)0.5 * dist, sup[2] - fr.n[2] * (T)0.5 * dist};
+  JBQ_EMIT(geom, x, dist);
+}
+
+// the four pyramid rows of a contact, from w = (J a - uref) in WORLD comps: n +- mu*t1, n +- mu*t2 (t1 = y, t2 = -x)
+template <typename T> JB_HD void jbq_rows(T* jar, const T* ww, T mu, T ar0) {
+  jar[0] = ww[2] + mu * ww[1] - ar0;
+  jar[1] = ww[2] - mu * ww[1] - ar0;
+  jar[2] = ww[2] - mu * ww[0] - ar0;
+  jar[3] = ww[2] + mu * ww[0] - ar0;
+}
+
+// u = J_c a in ROOT comps
+template <typename T> JB_HD void jbq_J_apply(T* u, const QCon<T>& c, const QVec<T>& a) {
+  T t[3];
+  cross3(t, a.r + 3, c.x);
+  T qa = c.kind == QK_ROTOR ? a.mo : a.la;
+  u[0] = a.r[0] + t[0] + c.ja[0] * qa + c.jb[0] * a.lb;
+  u[1] = a.r[1] + t[1] + c.ja[1] * qa + c.jb[1] * a.lb;
+  u[2] = a.r[2] + t[2] + c.ja[2] * qa + c.jb[2] * a.lb;
+}
+
+template <typename T> JB_HD void jbq_eval_ww(QConSet<T>& cs, const T* Rw, const QVec<T>& a) {
+  for (int i = 0; i < cs.n; i++) {
+    QCon<T>& c = cs.c[i];
+    T u[3], uw[3];
+    jbq_J_apply(u, c, a);
+    mulMV(uw, Rw, u);
+    c.ww[0] = uw[0] - c.uref[0]; c.ww[1] = uw[1] - c.uref[1]; c.ww[2] = uw[2] - c.uref[2];
+  }
+}
+
+template <typename T> JB_HD T jbq_cost(const QConSet<T>& cs, T mu) {
+  T cost = 0;
+  for (int i = 0; i < cs.n; i++) {
+    T jar[4];
+    jbq_rows(jar, cs.c[i].ww, mu, cs.c[i].ar0);
+#pragma unroll
+    for (int r = 0; r < 4; r++) if (jar[r] < (T)0) cost += (T)0.5 * cs.c[i].D * jar[r] * jar[r];
+  }
+  return cost;
+}
+
+// This lane's constraint forces at the current ww: writes the partial generalized force (root 6 + motor partial in
+// out[6], leg in *fla, *flb) and returns the lane's active-row mask (4 bits per contact).
+template <typename T>
+JB_HD uint32_t jbq_forces(const QConSet<T>& cs, const T* Rw, T mu, T* out7, T* fla, T* flb) {
+  uint32_t mask = 0;
+#pragma unroll
+  for (int i = 0; i < 7; i++) out7[i] = 0;
+  *fla = 0; *flb = 0;
+  for (int i = 0; i < cs.n; i++) {
+    const QCon<T>& c = cs.c[i];
+    T jar[4];
+    jbq_rows(jar, c.ww, mu, c.ar0);
+    T f0 = jar[0] < (T)0 ? -c.D * jar[0] : (T)0, f1 = jar[1] < (T)0 ? -c.D * jar[1] : (T)0;
+    T f2 = jar[2] < (T)0 ? -c.D * jar[2] : (T)0, f3 = jar[3] < (T)0 ? -c.D * jar[3] : (T)0;
+    mask |= ((jar[0] < (T)0 ? 1u : 0u) | (jar[1] < (T)0 ? 2u : 0u) | (jar[2] < (T)0 ? 4u : 0u) | (jar[3] < (T)0 ? 8u : 0u)) << (4 * i);
+    T fw[3] = {mu * (f3 - f2), mu * (f0 - f1), f0 + f1 + f2 + f3}, fr[3], t[3];
+    mulMTV(fr, Rw, fw);
+    out7[0] += fr[0]; out7[1] += fr[1]; out7[2] += fr[2];
+    cross3(t, c.x, fr);
+    out7[3] += t[0]; out7[4] += t[1]; out7[5] += t[2];
+    T ga = dot3(c.ja, fr), gb = dot3(c.jb, fr);
+    if (c.kind == QK_ROTOR) out7[6] += ga; else *fla += ga;
+    *flb += gb;
+  }
+  return mask;
+}
+
+// Hessian contact terms of this lane: leg block added to H in place, replicated block returned in part[28]
+template <typename T>
+JB_HD void jbq_hessian(QArrow<T>& H, T* part, const QConSet<T>& cs, const T* Rw, T mu) {
+#pragma unroll
+  for (int i = 0; i < 28; i++) part[i] = 0;
+  for (int i = 0; i < cs.n; i++) {
+    const QCon<T>& c = cs.c[i];
+    T jar[4];
+    jbq_rows(jar, c.ww, mu, c.ar0);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (!(jar[r] < (T)0)) continue;
+      T ew[3] = {r == 2 ? -mu : (r == 3 ? mu : (T)0), r == 0 ? mu : (r == 1 ? -mu : (T)0), (T)1}, e[3], j6[6];
+      mulMTV(e, Rw, ew);
+      j6[0] = e[0]; j6[1] = e[1]; j6[2] = e[2];
+      cross3(j6 + 3, c.x, e);
+      T d = c.D;
+#pragma unroll
+      for (int p = 0; p < 6; p++) {
+        T dp = d * j6[p];
+#pragma unroll
+        for (int q = 0; q <= p; q++) part[JBQ_TRI(p, q)] += dp * j6[q];
+      }
+      T jja = dot3(c.ja, e), jjb = dot3(c.jb, e);
+      if (c.kind == QK_ROTOR) {
+        part[27] += d * jja * jja;
+#pragma unroll
+        for (int p = 0; p < 6; p++) part[21 + p] += d * jja * j6[p];
+      } else {
+        H.aa += d * jja * jja; H.ab += d * jja * jjb; H.bb += d * jjb * jjb;
+#pragma unroll
+        for (int p = 0; p < 6; p++) { H.ca[p] += d * jja * j6[p]; H.cb[p] += d * jjb * j6[p]; }
+      }
+    }
+  }
+}
+
+// this lane's part of phi'(alpha) - (g1 + alpha g2) and of phi''(alpha) - g2; returns the active mask at alpha
+template <typename T> JB_HD uint32_t jbq_ls_local(const QConSet<T>& cs, T mu, T alpha, T* d_out, T* h_out) {
+  T d = 0, h = 0;
+  uint32_t mask = 0;
+  for (int i = 0; i < cs.n; i++) {
+    const QCon<T>& c = cs.c[i];
+    T jar[4], jv[4];
+    jbq_rows(jar, c.ww, mu, c.ar0);
+    jbq_rows(jv, c.jv, mu, (T)0);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      T x = jar[r] + alpha * jv[r];
+      if (x < (T)0) { d += c.D * x * jv[r]; h += c.D * jv[r] * jv[r]; mask |= 1u << (4 * i + r); }
+    }
+  }
+  *d_out = d; *h_out = h;
+  return mask;
+}
+
+// ------------------------------------------------------------------------------------------------ the sub-step (SPMD)
+// P: packed model (jb_packed.h); lane in [0,4).  forward_only: stop after the constraint solve (mj_forward).
+template <typename T, typename Comm>
+JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, bool forward_only, int* iter_accum,
+                       int* ncon_accum, int* overflow_accum, const QReport<T>* rep) {
+  const T* g = P;
+  const T* X = P + JBP_X + lane;
+  const T* L = P + JBP_L + lane;
+#define LX(i) X[4 * (i)]
+#define LL(i) L[4 * (i)]
+  const T h = g[G_H];
+  // ---------------- root frame (replicated)
+  QFrame<T> fr;
+  {
+    T qn = (T)1 / jb_sqrt(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
+    s.quat[0] *= qn; s.quat[1] *= qn; s.quat[2] *= qn; s.quat[3] *= qn;
+    quat2mat(fr.Rw, s.quat);
+  }
+  fr.pz = s.pos[2];
+  fr.n[0] = fr.Rw[6]; fr.n[1] = fr.Rw[7]; fr.n[2] = fr.Rw[8];
+  mulMTV(fr.vr, fr.Rw, s.vlin);
+  fr.w[0] = s.w[0]; fr.w[1] = s.w[1]; fr.w[2] = s.w[2];
+  const T* w = fr.w;
+  const T aO[3] = {g[G_GRAV] * fr.n[0], g[G_GRAV] * fr.n[1], g[G_GRAV] * fr.n[2]};   // fictitious -g at the root origin
+
+  QConSet<T> cs;
+  cs.n = 0; cs.overflow = 0;
+
+  // first moment / inertia about the origin and bias wrench: per-lane partials (this leg), summed over the quad below
+  T ht[3] = {0, 0, 0}, It[6] = {0, 0, 0, 0, 0, 0};
+  T bF[3] = {0, 0, 0}, bT[3] = {0, 0, 0};
+  auto accum_body = [&](T mass, const T* c, const T* Ic) {
+    addscl3(ht, c, mass);
+    T cc = dot3(c, c);
+    It[0] += Ic[0] + mass * (cc - c[0] * c[0]);
+    It[1] += Ic[1] + mass * (cc - c[1] * c[1]);
+    It[2] += Ic[2] + mass * (cc - c[2] * c[2]);
+    It[3] += Ic[3] - mass * c[0] * c[1];
+    It[4] += Ic[4] - mass * c[0] * c[2];
+    It[5] += Ic[5] - mass * c[1] * c[2];
+  };
+  auto acc_root_point = [&](T* a, const T* p) {
+    T t[3], u[3];
+    cross3(t, w, p); cross3(u, w, t);
+    a[0] = aO[0] + u[0]; a[1] = aO[1] + u[1]; a[2] = aO[2] + u[2];
+  };
+  auto acc_child = [&](T* out, const T* abase, const T* al, const T* om, const T* rr) {
+    T x1[3], x2[3], x3[3];
+    cross3(x1, al, rr); cross3(x2, om, rr); cross3(x3, om, x2);
+    out[0] = abase[0] + x1[0] + x3[0]; out[1] = abase[1] + x1[1] + x3[1]; out[2] = abase[2] + x1[2] + x3[2];
+  };
+  auto body_wrench = [&](T* F, T* N, T mass, const T* Ic, const T* acom, const T* om, const T* al) {
+    scl3(F, acom, mass);
+    T Iw[3], Ia[3], t[3];
+    mulSV(Iw, Ic, om); mulSV(Ia, Ic, al); cross3(t, om, Iw);
+    add3(N, Ia, t);
+  };
+
+  QArrow<T> Mx;
+  QVec<T> bias, fpass;
+  qv_zero(bias); qv_zero(fpass);
+
+  // ---------------- this lane's leg
+  T a1[3] = {LL(L_A1), LL(L_A1 + 1), LL(L_A1 + 2)}, p1[3] = {LL(L_P1), LL(L_P1 + 1), LL(L_P1 + 2)};
+  T a2[3], p2[3];
+  {
+    T a2h[3] = {LL(L_A2), LL(L_A2 + 1), LL(L_A2 + 2)}, p2h[3] = {LL(L_P2), LL(L_P2 + 1), LL(L_P2 + 2)};
+    T sa, ca, sb, cb;
+    jb_sincos(s.qa, &sa, &ca);
+    jb_sincos(s.qb, &sb, &cb);
+    T R1[9], R2[9], R12[9];
+    rodrigues(R1, a1, sa, ca);
+    rodrigues(R2, a2h, sb, cb);
+    mulMM(R12, R1, R2);
+    T t[3], r[3], tmp[3], tmp2[3];
+    mulMV(a2, R1, a2h);
+    sub3(r, p2h, p1); mulMV(t, R1, r); add3(p2, p1, t);
+    T cu[3], cl[3], Iu[6], Il[6], ch[3], Ih[6];
+    ch[0] = LL(L_CU); ch[1] = LL(L_CU + 1); ch[2] = LL(L_CU + 2);
+    sub3(r, ch, p1); mulMV(t, R1, r); add3(cu, p1, t);
+    ch[0] = LL(L_CL); ch[1] = LL(L_CL + 1); ch[2] = LL(L_CL + 2);
+    sub3(r, ch, p2h); mulMV(t, R12, r); add3(cl, p2, t);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Ih[i] = LL(L_IU + i);
+    rotSym(Iu, R1, Ih);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Ih[i] = LL(L_IL + i);
+    rotSym(Il, R12, Ih);
+    const T mu_ = LL(L_MU), ml_ = LL(L_ML);
+    accum_body(mu_, cu, Iu);
+    accum_body(ml_, cl, Il);
+    // inertia columns: P = sum m a x (c - p), L = sum (I a + c x P_b)
+    T Pb[3], Lb[3], Pa[3], La[3], Pal[3], Pau[3];
+    sub3(r, cl, p2); cross3(tmp, a2, r); scl3(Pb, tmp, ml_);
+    mulSV(tmp, Il, a2); cross3(tmp2, cl, Pb); add3(Lb, tmp, tmp2);
+    sub3(r, cl, p1); cross3(tmp, a1, r); scl3(Pal, tmp, ml_);
+    sub3(r, cu, p1); cross3(tmp, a1, r); scl3(Pau, tmp, mu_);
+    add3(Pa, Pal, Pau);
+    mulSV(La, Il, a1); mulSV(tmp, Iu, a1); addto3(La, tmp);
+    cross3(tmp, cl, Pal); addto3(La, tmp);
+    cross3(tmp, cu, Pau); addto3(La, tmp);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { Mx.cb[i] = Pb[i]; Mx.cb[3 + i] = Lb[i]; Mx.ca[i] = Pa[i]; Mx.ca[3 + i] = La[i]; }
+    cross3(tmp, p2, Pb); sub3(tmp2, Lb, tmp); Mx.bb = dot3(a2, tmp2);
+    cross3(tmp, p1, Pb); sub3(tmp2, Lb, tmp); Mx.ab = dot3(a1, tmp2);
+    cross3(tmp, p1, Pa); sub3(tmp2, La, tmp); Mx.aa = dot3(a1, tmp2);
+    // Newton-Euler bias
+    T om1[3], al1[3], om2[3], al2[3], ap1[3], ap2[3], acu[3], acl[3];
+    om1[0] = w[0] + a1[0] * s.va; om1[1] = w[1] + a1[1] * s.va; om1[2] = w[2] + a1[2] * s.va;
+    cross3(al1, w, a1); scl3(al1, al1, s.va);
+    om2[0] = om1[0] + a2[0] * s.vb; om2[1] = om1[1] + a2[1] * s.vb; om2[2] = om1[2] + a2[2] * s.vb;
+    cross3(tmp, om1, a2);
+    al2[0] = al1[0] + tmp[0] * s.vb; al2[1] = al1[1] + tmp[1] * s.vb; al2[2] = al1[2] + tmp[2] * s.vb;
+    acc_root_point(ap1, p1);
+    T ru[3], r12[3], rl[3];
+    sub3(ru, cu, p1); acc_child(acu, ap1, al1, om1, ru);
+    sub3(r12, p2, p1); acc_child(ap2, ap1, al1, om1, r12);
+    sub3(rl, cl, p2); acc_child(acl, ap2, al2, om2, rl);
+    T Fu[3], Nu[3], Fl[3], Nl[3];
+    body_wrench(Fu, Nu, mu_, Iu, acu, om1, al1);
+    body_wrench(Fl, Nl, ml_, Il, acl, om2, al2);
+    cross3(tmp, rl, Fl); addto3(tmp, Nl); bias.lb = dot3(a2, tmp);
+    cross3(tmp, ru, Fu); addto3(tmp, Nu);
+    sub3(r, cl, p1); cross3(tmp2, r, Fl); addto3(tmp, tmp2); addto3(tmp, Nl);
+    bias.la = dot3(a1, tmp);
+    bF[0] = Fu[0] + Fl[0]; bF[1] = Fu[1] + Fl[1]; bF[2] = Fu[2] + Fl[2];
+    cross3(tmp, cu, Fu); cross3(tmp2, cl, Fl);
+    bT[0] = tmp[0] + tmp2[0] + Nu[0] + Nl[0]; bT[1] = tmp[1] + tmp2[1] + Nu[1] + Nl[1]; bT[2] = tmp[2] + tmp2[2] + Nu[2] + Nl[2];
+    fpass.la = -LL(L_K1) * s.qa - LL(L_D1) * s.va;
+    fpass.lb = -LL(L_K2) * s.qb - LL(L_D2) * s.vb;
+    // collision: this leg's geoms.  Cheap height test on the sphere centres / cylinder bounding spheres first.
+    {
+      QBody<T> bu = {QK_LEG, a1, p1, s.va, a2, p2, (T)0, false, LL(L_INVWU)};
+      QBody<T> bl = {QK_LEG, a1, p1, s.va, a2, p2, s.vb, true, LL(L_INVWL)};
+      T c[3], gh[3], gv[3], ax[3], xa[3];
+      // foot sphere (lower body)
+      gh[0] = LL(L_FT_C); gh[1] = LL(L_FT_C + 1); gh[2] = LL(L_FT_C + 2);
+      sub3(r, gh, p2h); mulMV(t, R12, r); add3(c, p2, t);
+      jbq_col_sphere<T>(g, cs, fr, bl, (int)LL(L_FT_ID), c, LL(L_FT_R), rep, lane);
+      // lower cylinder
+      gh[0] = LL(L_LC_C); gh[1] = LL(L_LC_C + 1); gh[2] = LL(L_LC_C + 2);
+      sub3(r, gh, p2h); mulMV(t, R12, r); add3(c, p2, t);
+      {
+        T rr_ = LL(L_LC_R), hl_ = LL(L_LC_HL);
+        if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+          gv[0] = LL(L_LC_AX); gv[1] = LL(L_LC_AX + 1); gv[2] = LL(L_LC_AX + 2); mulMV(ax, R12, gv);
+          gv[0] = LL(L_LC_XA); gv[1] = LL(L_LC_XA + 1); gv[2] = LL(L_LC_XA + 2); mulMV(xa, R12, gv);
+          jbq_col_cylinder<T>(g, cs, fr, bl, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
+        }
+      }
+      // knee sphere (upper body)
+      gh[0] = LL(L_KN_C); gh[1] = LL(L_KN_C + 1); gh[2] = LL(L_KN_C + 2);
+      sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
+      jbq_col_sphere<T>(g, cs, fr, bu, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane);
+      // upper cylinder
+      gh[0] = LL(L_UC_C); gh[1] = LL(L_UC_C + 1); gh[2] = LL(L_UC_C + 2);
+      sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
+      {
+        T rr_ = LL(L_UC_R), hl_ = LL(L_UC_HL);
+        if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+          gv[0] = LL(L_UC_AX); gv[1] = LL(L_UC_AX + 1); gv[2] = LL(L_UC_AX + 2); mulMV(ax, R1, gv);
+          gv[0] = LL(L_UC_XA); gv[1] = LL(L_UC_XA + 1); gv[2] = LL(L_UC_XA + 2); mulMV(xa, R1, gv);
+          jbq_col_cylinder<T>(g, cs, fr, bu, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+        }
+      }
+    }
+  }
+
+  // ---------------- quad-sum the leg partials: first moment (3), origin inertia (6), bias force/torque (6)
+  {
+    T red[15] = {ht[0], ht[1], ht[2], It[0], It[1], It[2], It[3], It[4], It[5], bF[0], bF[1], bF[2], bT[0], bT[1], bT[2]};
+    cm.sumN(red, 15);
+    ht[0] = red[0]; ht[1] = red[1]; ht[2] = red[2];
+#pragma unroll
+    for (int i = 0; i < 6; i++) It[i] = red[3 + i];
+    bias.r[0] = red[9]; bias.r[1] = red[10]; bias.r[2] = red[11]; bias.r[3] = red[12]; bias.r[4] = red[13]; bias.r[5] = red[14];
+  }
+
+  // ---------------- root (core) body and rotor: replicated in the 4 lanes
+  T pm[3] = {g[G_PM], g[G_PM + 1], g[G_PM + 2]}, am[3] = {g[G_AM], g[G_AM + 1], g[G_AM + 2]};
+  T Rm[9];
+  {
+    T c0[3] = {g[G_C0], g[G_C0 + 1], g[G_C0 + 2]}, I0[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) I0[i] = g[G_I0 + i];
+    accum_body(g[G_M0], c0, I0);
+    T ac[3], F[3], N[3], zero[3] = {0, 0, 0}, t[3];
+    acc_root_point(ac, c0);
+    body_wrench(F, N, g[G_M0], I0, ac, w, zero);
+    bias.r[0] += F[0]; bias.r[1] += F[1]; bias.r[2] += F[2];
+    cross3(t, c0, F);
+    bias.r[3] += t[0] + N[0]; bias.r[4] += t[1] + N[1]; bias.r[5] += t[2] + N[2];
+    // rotor
+    T sm, cmn, r[3], cmc[3], Imc[6], ch[3] = {g[G_CM], g[G_CM + 1], g[G_CM + 2]}, Ih[6];
+    jb_sincos(s.qm, &sm, &cmn);
+    rodrigues(Rm, am, sm, cmn);
+    sub3(r, ch, pm); mulMV(t, Rm, r); add3(cmc, pm, t);
+#pragma unroll
+    for (int i = 0; i < 6; i++) Ih[i] = g[G_IM + i];
+    rotSym(Imc, Rm, Ih);
+    const T mm_ = g[G_MM];
+    accum_body(mm_, cmc, Imc);
+    T Pv[3], Lv[3], tmp[3], tmp2[3];
+    sub3(r, cmc, pm); cross3(tmp, am, r); scl3(Pv, tmp, mm_);
+    mulSV(Lv, Imc, am); cross3(tmp, cmc, Pv); addto3(Lv, tmp);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { Mx.cm[i] = Pv[i]; Mx.cm[3 + i] = Lv[i]; }
+    cross3(tmp, pm, Pv); sub3(tmp2, Lv, tmp); Mx.mm = dot3(am, tmp2);
+    T om[3], al[3], ap[3];
+    om[0] = w[0] + am[0] * s.vm; om[1] = w[1] + am[1] * s.vm; om[2] = w[2] + am[2] * s.vm;
+    cross3(al, w, am); scl3(al, al, s.vm);
+    acc_root_point(ap, pm);
+    acc_child(ac, ap, al, om, r);
+    body_wrench(F, N, mm_, Imc, ac, om, al);
+    cross3(tmp, r, F); addto3(tmp, N); bias.mo = dot3(am, tmp);
+    bias.r[0] += F[0]; bias.r[1] += F[1]; bias.r[2] += F[2];
+    cross3(tmp, cmc, F);
+    bias.r[3] += tmp[0] + N[0]; bias.r[4] += tmp[1] + N[1]; bias.r[5] += tmp[2] + N[2];
+    T u = jb_min(g[G_CHI], jb_max(g[G_CLO], ctrl));
+    T force = g[G_GAIN] * u + g[G_BIASV] * (g[G_GEAR] * s.vm);
+    fpass.mo = g[G_GEAR] * force - g[G_DAMPM] * s.vm;
+  }
+  // root block of M
+  {
+    const T mt = g[G_MTOT];
+#pragma unroll
+    for (int i = 0; i < 21; i++) Mx.R[i] = 0;
+    Mx.R[JBQ_TRI(0, 0)] = mt; Mx.R[JBQ_TRI(1, 1)] = mt; Mx.R[JBQ_TRI(2, 2)] = mt;
+    Mx.R[JBQ_TRI(3, 1)] = -ht[2]; Mx.R[JBQ_TRI(3, 2)] = ht[1];
+    Mx.R[JBQ_TRI(4, 0)] = ht[2];  Mx.R[JBQ_TRI(4, 2)] = -ht[0];
+    Mx.R[JBQ_TRI(5, 0)] = -ht[1]; Mx.R[JBQ_TRI(5, 1)] = ht[0];
+    Mx.R[JBQ_TRI(3, 3)] = It[0]; Mx.R[JBQ_TRI(4, 4)] = It[1]; Mx.R[JBQ_TRI(5, 5)] = It[2];
+    Mx.R[JBQ_TRI(4, 3)] = It[3]; Mx.R[JBQ_TRI(5, 3)] = It[4]; Mx.R[JBQ_TRI(5, 4)] = It[5];
+  }
+
+  // ---------------- collision of the extra geoms: lanes 0,1 -> core boxes; lane 2 -> root cylinder + ellipsoid;
+  //                  lane 3 -> rotor cylinder + ellipsoid
+  if (lane < 2) {
+    T c[3] = {LX(X_BOX_C), LX(X_BOX_C + 1), LX(X_BOX_C + 2)}, half[3] = {LX(X_BOX_H), LX(X_BOX_H + 1), LX(X_BOX_H + 2)};
+    if (fr.pz + dot3(fr.n, c) - jb_sqrt(dot3(half, half)) <= (T)0) {
+      T Rg[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rg[i] = LX(X_BOX_R + i);
+      QBody<T> b = {QK_ROOT, nullptr, nullptr, (T)0, nullptr, nullptr, (T)0, false, g[G_INVW0]};
+      jbq_col_box<T>(g, cs, fr, b, (int)LX(X_BOX_ID), c, Rg, half, rep, lane);
+    }
+  } else {
+    const bool rotor = lane == 3;
+    QBody<T> b = {rotor ? QK_ROTOR : QK_ROOT, am, pm, rotor ? s.vm : (T)0, nullptr, nullptr, (T)0, false,
+                  rotor ? g[G_INVWM] : g[G_INVW0]};
+    T ch[3] = {LX(X_CYL_C), LX(X_CYL_C + 1), LX(X_CYL_C + 2)}, c[3], r[3], t[3];
+    if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
+    T rr_ = LX(X_CYL_R), hl_ = LX(X_CYL_HL);
+    if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+      T gv[3] = {LX(X_CYL_AX), LX(X_CYL_AX + 1), LX(X_CYL_AX + 2)}, gx[3] = {LX(X_CYL_XA), LX(X_CYL_XA + 1), LX(X_CYL_XA + 2)};
+      T ax[3], xa[3];
+      if (rotor) { mulMV(ax, Rm, gv); mulMV(xa, Rm, gx); }
+      else { ax[0] = gv[0]; ax[1] = gv[1]; ax[2] = gv[2]; xa[0] = gx[0]; xa[1] = gx[1]; xa[2] = gx[2]; }
+      jbq_col_cylinder<T>(g, cs, fr, b, (int)LX(X_CYL_ID), c, ax, xa, rr_, hl_, rep, lane);
+    }
+    ch[0] = LX(X_ELL_C); ch[1] = LX(X_ELL_C + 1); ch[2] = LX(X_ELL_C + 2);
+    if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
+    T sz[3] = {LX(X_ELL_S), LX(X_ELL_S + 1), LX(X_ELL_S + 2)};
+    if (fr.pz + dot3(fr.n, c) - jb_max(sz[0], jb_max(sz[1], sz[2])) <= (T)0) {
+      T Rh[9], Rg[9];
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rh[i] = LX(X_ELL_R + i);
+      if (rotor) mulMM(Rg, Rm, Rh);
+      else {
+#pragma unroll
+        for (int i = 0; i < 9; i++) Rg[i] = Rh[i];
+      }
+      jbq_col_ellipsoid<T>(g, cs, fr, b, (int)LX(X_ELL_ID), c, Rg, sz, rep, lane);
+    }
+  }
+
+  // ---------------- smooth dynamics: f_s = passive + actuator - bias ; a_s = M^-1 f_s
+  QVec<T> fs = fpass;
+  qv_axpy(fs, (T)-1, bias);
+  QVec<T> as_;
+  QArrow<T> FM = Mx;
+  qarrow_factor<T, Comm>(cm, FM, nullptr);
+  qarrow_solve(cm, as_, FM, fs);
+
+  const int ncon = cm.isum(cs.n);
+
+  // ---------------- constraint solve (primal Newton)
+  QVec<T> a = as_;
+  int iters = 0;
+  const T mu = g[G_FRIC];
+  if (ncon > 0) {
+    QVec<T> aw;
+    {
+      T lw[3] = {s.wr[0], s.wr[1], s.wr[2]}, lr[3];
+      mulMTV(lr, fr.Rw, lw);
+      aw.r[0] = lr[0]; aw.r[1] = lr[1]; aw.r[2] = lr[2]; aw.r[3] = s.wr[3]; aw.r[4] = s.wr[4]; aw.r[5] = s.wr[5];
+      aw.la = s.wla; aw.lb = s.wlb; aw.mo = s.wmo;
+    }
+    QVec<T> Ma;
+    qarrow_mul(cm, Ma, Mx, aw);
+    // total cost at the warm start and at the unconstrained acceleration (mj_fwdConstraint warmstart selection)
+    QVec<T> res = Ma; qv_axpy(res, (T)-1, fs);
+    QVec<T> da = aw; qv_axpy(da, (T)-1, as_);
+    jbq_eval_ww(cs, fr.Rw, aw);
+    T cw = jbq_cost(cs, mu) + (T)0.5 * qv_dot_leg(res, da);
+    jbq_eval_ww(cs, fr.Rw, as_);
+    T csm = jbq_cost(cs, mu);
+    cm.sum2(cw, csm);
+    cw += (T)0.5 * qv_dot_rep(res, da);
+    if (cw > csm) {
+      a = as_; Ma = fs;                 // M a_s = f_s ; ww already evaluated at a_s
+    } else {
+      a = aw;
+      jbq_eval_ww(cs, fr.Rw, a);
+    }
+    const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
+    T f7[7], fla, flb;
+    uint32_t mask = jbq_forces(cs, fr.Rw, mu, f7, &fla, &flb);
+    cm.sumN(f7, 7);
+    QVec<T> grad = Ma;
+    qv_axpy(grad, (T)-1, fs);
+#pragma unroll
+    for (int i = 0; i < 6; i++) grad.r[i] -= f7[i];
+    grad.la -= fla; grad.lb -= flb; grad.mo -= f7[6];
+    const int maxit = JbEps<T>::newton_iters();
+    while (iters < maxit) {
+      QArrow<T> H = Mx;
+      T part[28];
+      jbq_hessian(H, part, cs, fr.Rw, mu);
+      qarrow_factor<T, Comm>(cm, H, part);
+      QVec<T> search;
+      qarrow_solve(cm, search, H, grad);
+#pragma unroll
+      for (int i = 0; i < 6; i++) search.r[i] = -search.r[i];
+      search.la = -search.la; search.lb = -search.lb; search.mo = -search.mo;
+      QVec<T> Mv;
+      qarrow_mul(cm, Mv, Mx, search);
+      for (int i = 0; i < cs.n; i++) {
+        T u[3];
+        jbq_J_apply(u, cs.c[i], search);
+        mulMV(cs.c[i].jv, fr.Rw, u);
+      }
+      res = Ma; qv_axpy(res, (T)-1, fs);
+      // g1 = s.(Ma - fs), g2 = s.Mv, d0 = s.grad (= phi'(0)); at alpha = 1: contact part of phi' and phi''
+      T red[6];
+      red[0] = qv_dot_leg(search, res); red[1] = qv_dot_leg(search, Mv); red[2] = qv_dot_leg(search, grad);
+      uint32_t m1 = jbq_ls_local(cs, mu, (T)1, &red[3], &red[4]);
+      red[5] = m1 == mask ? (T)0 : (T)1;
+      cm.sumN(red, 6);
+      T g1 = red[0] + qv_dot_rep(search, res), g2 = red[1] + qv_dot_rep(search, Mv), d0 = red[2] + qv_dot_rep(search, grad);
+      if (!(d0 < (T)0)) break;                           // not a descent direction: converged to rounding
+      T alpha = 1;
+      bool full = red[5] == (T)0;                        // same active set at alpha = 1: the Newton step is exact
+      if (!full) {
+        T d = g1 + g2 + red[3], dd = g2 + red[4];
+        T lo = 0, hi = -1, tol = JbEps<T>::ls_tol() * jb_abs(d0);
+        for (int it = 0; it < 30; it++) {
+          if (jb_abs(d) <= tol) break;
+          if (d < (T)0) lo = alpha; else hi = alpha;
+          T an = alpha - d / dd;
+          if (hi > (T)0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+          else if (!(an > lo)) an = alpha * (T)2;
+          if (an == alpha) break;
+          alpha = an;
+          T dl, hl;
+          jbq_ls_local(cs, mu, alpha, &dl, &hl);
+          cm.sum2(dl, hl);
+          d = g1 + alpha * g2 + dl; dd = g2 + hl;
+        }
+      }
+      qv_axpy(a, alpha, search);
+      qv_axpy(Ma, alpha, Mv);
+      for (int i = 0; i < cs.n; i++) {
+        QCon<T>& c = cs.c[i];
+        c.ww[0] += alpha * c.jv[0]; c.ww[1] += alpha * c.jv[1]; c.ww[2] += alpha * c.jv[2];
+      }
+      T f8[8];
+      uint32_t newmask = jbq_forces(cs, fr.Rw, mu, f8, &fla, &flb);
+      f8[7] = newmask == mask ? (T)0 : (T)1;
+      mask = newmask;
+      cm.sumN(f8, 8);
+      grad = Ma;
+      qv_axpy(grad, (T)-1, fs);
+#pragma unroll
+      for (int i = 0; i < 6; i++) grad.r[i] -= f8[i];
+      grad.la -= fla; grad.lb -= flb; grad.mo -= f8[6];
+      iters++;
+      T gl = qv_dot_leg(grad, grad);
+      gl = cm.sum(gl);
+      T gn = scale * jb_sqrt(gl + qv_dot_rep(grad, grad));
+      if ((full && f8[7] == (T)0) || gn < JbEps<T>::newton_tol()) break;
+    }
+  }
+  if (iter_accum) *iter_accum += iters;
+  if (ncon_accum) *ncon_accum += ncon;
+  if (overflow_accum) *overflow_accum += cm.isum(cs.overflow);
+
+  // ---------------- save warm start (MuJoCo coordinates)
+  {
+    T lw[3];
+    mulMV(lw, fr.Rw, a.r);
+    s.wr[0] = lw[0]; s.wr[1] = lw[1]; s.wr[2] = lw[2]; s.wr[3] = a.r[3]; s.wr[4] = a.r[4]; s.wr[5] = a.r[5];
+    s.wla = a.la; s.wlb = a.lb; s.wmo = a.mo;
+  }
+  if (forward_only) return;
+
+  // ---------------- semi-implicit Euler, implicit in joint damping: (M + hB) a' = f_s + f_c.  At the solver's fixed
+  // point f_s + f_c = M a, so a' = a - (M + hB)^-1 (hB a) = a - M^-1 (hB a) + O((hB/M)^2 a): hB/M ~ 1e-3 on the leg
+  // dofs, i.e. a relative error ~1e-6 of a 1e-3 correction.  Reuses the factor of M from the smooth solve.
+  {
+    // Neumann series a' = sum_k (-M^-1 hB)^k a: one term is below fp32 resolution, fp64 (test build) takes four
+    const int nterms = sizeof(T) == 8 ? 4 : 1;
+    QVec<T> term = a;
+    T sign = (T)-1;
+    for (int k = 0; k < nterms; k++) {
+      QVec<T> hb, dl;
+      qv_zero(hb);
+      hb.la = h * LL(L_D1) * term.la; hb.lb = h * LL(L_D2) * term.lb; hb.mo = h * g[G_DAMPM] * term.mo;
+      qarrow_solve(cm, dl, FM, hb);
+      qv_axpy(a, sign, dl);
+      term = dl;
+      sign = -sign;
+    }
+  }
+  {
+    T lw[3];
+    mulMV(lw, fr.Rw, a.r);
+    s.vlin[0] += h * lw[0]; s.vlin[1] += h * lw[1]; s.vlin[2] += h * lw[2];
+    s.w[0] += h * a.r[3]; s.w[1] += h * a.r[4]; s.w[2] += h * a.r[5];
+    s.va += h * a.la; s.vb += h * a.lb; s.vm += h * a.mo;
+  }
+  s.pos[0] += h * s.vlin[0]; s.pos[1] += h * s.vlin[1]; s.pos[2] += h * s.vlin[2];
+  {
+    T wn = jb_sqrt(s.w[0] * s.w[0] + s.w[1] * s.w[1] + s.w[2] * s.w[2]);
+    T ax[3] = {1, 0, 0};
+    T ang = 0;
+    if (wn >= (T)1e-15) { ax[0] = s.w[0] / wn; ax[1] = s.w[1] / wn; ax[2] = s.w[2] / wn; ang = h * wn; }
+    T sh, ch;
+    jb_sincos((T)0.5 * ang, &sh, &ch);
+    T q[4] = {s.quat[0], s.quat[1], s.quat[2], s.quat[3]};
+    T dq[4] = {ch, ax[0] * sh, ax[1] * sh, ax[2] * sh};
+    s.quat[0] = q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2] - q[3] * dq[3];
+    s.quat[1] = q[0] * dq[1] + q[1] * dq[0] + q[2] * dq[3] - q[3] * dq[2];
+    s.quat[2] = q[0] * dq[2] - q[1] * dq[3] + q[2] * dq[0] + q[3] * dq[1];
+    s.quat[3] = q[0] * dq[3] + q[1] * dq[2] - q[2] * dq[1] + q[3] * dq[0];
+  }
+  s.qa += h * s.va; s.qb += h * s.vb;
+  s.qm += h * s.vm;
+  if (s.qm > (T)3.14159265358979323846) { s.qm -= (T)6.28318530717958647692; s.rev += 1; }
+  else if (s.qm <= -(T)3.14159265358979323846) { s.qm += (T)6.28318530717958647692; s.rev -= 1; }
+#undef LX
+#undef LL
+}
+
+#endif  // JB_QUAD_CUH

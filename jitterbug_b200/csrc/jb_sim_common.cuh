@@ -1,24 +1,25 @@
-// Shared declarations of the simulator's translation units: device-side state layout and the launcher of the
-// fused step / reset / contact-report kernel (instantiated once per model mode in its own .cu so the two heavy
-// instantiations compile in parallel).
+// Shared declarations of the simulator's translation units: device-side state layout and the launcher of the fused
+// step / reset / contact-report kernel.
 #ifndef JB_SIM_COMMON_CUH
 #define JB_SIM_COMMON_CUH
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "../../include/jbsim.h"
-#include "jb_task.cuh"
+#include "jb_packed.h"
 
-#define JB_BLOCK 128
+#define JB_BLOCK 128                 /* threads per CTA = 32 quads = 32 envs */
+#define JB_ENVS_PER_BLOCK (JB_BLOCK / 4)
 
-// HBM layout: struct-of-arrays, env index fastest, so a warp's 32 envs load/store each state component as one
-// 128-byte line:  qpos[16][N] (motor angle wrapped, revolutions in rev[N]), qvel[15][N], warm[15][N],
-// target[4][N], task[N], step_count[N], episode[N], reset_next[N].
+// HBM layout: struct-of-arrays, env index fastest: qpos[16][N] (motor angle wrapped, revolutions in rev[N]),
+// qvel[15][N], warm[15][N], target[4][N], task[N], step_count[N], episode[N], reset_next[N].  A warp holds 8 envs, so
+// each replicated (root / motor) component is one 32-byte sector per warp and each leg component four of them.
 struct JbDev {
   float *qpos, *qvel, *warm, *target;
   int *rev, *task, *step_count, *episode;
   unsigned char* reset_next;
   unsigned long long* counters;     // 5
-  const JbModel* models;            // per-env models or nullptr
+  const float* packed;              // [JBP_SIZE] (shared model) or [N][JBP_SIZE] (per-env models)
+  int per_env;
   int N, n_sub, step_limit, random_pose, obs_stride;
   unsigned long long seed;
   unsigned int env_id_offset;
@@ -31,9 +32,9 @@ struct JbLaunchArgs {
   const unsigned char* mask;        // RESET: optional per-env mask
   const float* actions;             // STEP
   float* obs; float* reward; int* step_type;
-  int* ncon; int* geom; float* dist; int max_con;   // CONTACTS
+  int* rep_geom; float* rep_dist;   // CONTACTS: staging [N][4*JBQ_CAP]
 };
 
-cudaError_t jb_launch_shared(const JbModel& shared, const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
-cudaError_t jb_launch_perenv(const JbModel& shared, const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
+cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
+cudaError_t jb_configure_kernels(void);   // per device: opt in to the dynamic shared memory the per-env mode needs
 #endif

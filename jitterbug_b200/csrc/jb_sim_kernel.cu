@@ -1,0 +1,196 @@
+// The fused kernel (sm_100a): one QUAD of lanes per environment runs a whole control step -- n_sub_steps physics
+// sub-steps + reward + observation + episode bookkeeping -- without touching HBM in between.  CTA = 128 threads = 32
+// envs; the packed model sits in shared memory (one copy per CTA for the shared model, one per env for augmented
+// models).  See jb_quad.cuh for the per-quad algorithm and DESIGN.md for the roofline model.
+#include "jb_sim_common.cuh"
+#include "jb_quad.cuh"
+#include "jb_task.cuh"
+
+struct QuadCommGPU {
+  unsigned mask;
+  __device__ __forceinline__ float sum(float v) {
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    return v;
+  }
+  __device__ __forceinline__ void sum2(float& a, float& b) { a = sum(a); b = sum(b); }
+  __device__ __forceinline__ void sumN(float* v, int n) {
+#pragma unroll
+    for (int i = 0; i < 28; i++) if (i < n) v[i] = sum(v[i]);
+  }
+  __device__ __forceinline__ int isum(int v) {
+    v += __shfl_xor_sync(mask, v, 1);
+    v += __shfl_xor_sync(mask, v, 2);
+    return v;
+  }
+};
+
+__device__ __forceinline__ void load_state(const JbDev& d, int e, int lane, QState<float>& s) {
+  const int N = d.N;
+  s.pos[0] = d.qpos[0 * N + e]; s.pos[1] = d.qpos[1 * N + e]; s.pos[2] = d.qpos[2 * N + e];
+#pragma unroll
+  for (int i = 0; i < 4; i++) s.quat[i] = d.qpos[(3 + i) * N + e];
+  s.qa = d.qpos[(7 + 2 * lane) * N + e]; s.qb = d.qpos[(8 + 2 * lane) * N + e];
+  s.qm = d.qpos[15 * N + e];
+  s.rev = d.rev[e];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { s.vlin[i] = d.qvel[i * N + e]; s.w[i] = d.qvel[(3 + i) * N + e]; }
+  s.va = d.qvel[(6 + 2 * lane) * N + e]; s.vb = d.qvel[(7 + 2 * lane) * N + e];
+  s.vm = d.qvel[14 * N + e];
+#pragma unroll
+  for (int i = 0; i < 6; i++) s.wr[i] = d.warm[i * N + e];
+  s.wla = d.warm[(6 + 2 * lane) * N + e]; s.wlb = d.warm[(7 + 2 * lane) * N + e];
+  s.wmo = d.warm[14 * N + e];
+}
+
+__device__ __forceinline__ void store_state(const JbDev& d, int e, int lane, const QState<float>& s) {
+  const int N = d.N;
+  d.qpos[(7 + 2 * lane) * N + e] = s.qa; d.qpos[(8 + 2 * lane) * N + e] = s.qb;
+  d.qvel[(6 + 2 * lane) * N + e] = s.va; d.qvel[(7 + 2 * lane) * N + e] = s.vb;
+  d.warm[(6 + 2 * lane) * N + e] = s.wla; d.warm[(7 + 2 * lane) * N + e] = s.wlb;
+  // replicated components: spread the stores over the four lanes
+  if (lane == 0) {
+    d.qpos[0 * N + e] = s.pos[0]; d.qpos[1 * N + e] = s.pos[1]; d.qpos[2 * N + e] = s.pos[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) d.qpos[(3 + i) * N + e] = s.quat[i];
+  } else if (lane == 1) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { d.qvel[i * N + e] = s.vlin[i]; d.qvel[(3 + i) * N + e] = s.w[i]; }
+  } else if (lane == 2) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) d.warm[i * N + e] = s.wr[i];
+  } else {
+    d.qpos[15 * N + e] = s.qm; d.rev[e] = s.rev; d.qvel[14 * N + e] = s.vm; d.warm[14 * N + e] = s.wmo;
+  }
+}
+
+__device__ __forceinline__ bool state_bad(const QState<float>& s) {
+  float acc = fabsf(s.qa) + fabsf(s.qb) + fabsf(s.va) + fabsf(s.vb) + fabsf(s.qm) + fabsf(s.vm);
+#pragma unroll
+  for (int i = 0; i < 3; i++) acc += fabsf(s.pos[i]) + fabsf(s.vlin[i]) + fabsf(s.w[i]);
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc += fabsf(s.quat[i]);
+  return !(acc < 1e10f);      // NaN or huge (mj_checkPos / mj_checkVel threshold)
+}
+
+__device__ __forceinline__ void do_reset(const float* g, const JbDev& d, int e, int lane, QState<float>& s,
+                                         JbTarget<float>& tg, int task) {
+  int ep = d.episode[e];
+  jb_reset_env<float>(g, s, tg, task, d.random_pose, d.seed, d.env_id_offset + (unsigned)e, (unsigned)ep);
+  s.qa = s.qb = s.va = s.vb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; i++) s.wr[i] = 0.f;
+  s.wla = s.wlb = s.wmo = 0.f;
+  __syncwarp(0xFu << (threadIdx.x & 28));       // all four lanes have read episode[e] before lane 0 bumps it
+  if (lane == 0) {
+    d.episode[e] = ep + 1;
+    d.step_count[e] = 0;
+    d.reset_next[e] = 0;
+    const int N = d.N;
+    d.target[0 * N + e] = tg.x; d.target[1 * N + e] = tg.y; d.target[2 * N + e] = tg.qw; d.target[3 * N + e] = tg.qz;
+  }
+}
+
+__device__ __forceinline__ void write_obs(const float* g, const JbDev& d, int e, const QState<float>& s, int task,
+                                          const JbTarget<float>& tg, float* obs_out, float* reward_out) {
+  float obs[JB_OBS_MAX], rew;
+  int n = jb_obs_reward<float>(g, s, task, tg, obs, &rew);
+  if (obs_out) {
+    float* o = obs_out + (size_t)e * d.obs_stride;
+#pragma unroll
+    for (int i = 0; i < JB_OBS_MAX; i++)
+      if (i < d.obs_stride) o[i] = i < n ? obs[i] : 0.f;
+  }
+  if (reward_out) reward_out[e] = rew;
+}
+
+extern __shared__ float jb_smem[];
+
+__global__ void __launch_bounds__(JB_BLOCK)
+jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchArgs a) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 3;
+  const int e = blockIdx.x * JB_ENVS_PER_BLOCK + (tid >> 2);
+  // ---- packed model -> shared memory
+  if (d.per_env) {
+    const int e0 = blockIdx.x * JB_ENVS_PER_BLOCK;
+    const int nenv = min(JB_ENVS_PER_BLOCK, d.N - e0);
+    const float* src = d.packed + (size_t)e0 * JBP_SIZE;
+    for (int i = tid; i < nenv * JBP_SIZE; i += JB_BLOCK) jb_smem[i] = src[i];
+  } else {
+    for (int i = tid; i < JBP_SIZE; i += JB_BLOCK) jb_smem[i] = d.packed[i];
+  }
+  __syncthreads();
+  if (e >= d.N) return;
+  const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_SIZE : jb_smem;
+  QuadCommGPU cm;
+  cm.mask = 0xFu << ((tid & 31) & 28);
+  const int N = d.N;
+  const int task = d.task[e];
+  QState<float> s;
+  JbTarget<float> tg;
+  const bool reset_now = a.mode == JB_MODE_RESET ? (!a.mask || a.mask[e]) : (a.mode == JB_MODE_STEP && d.reset_next[e]);
+  if (a.mode == JB_MODE_RESET && !reset_now) return;
+  int iters = 0, ncon_sum = 0, overflow = 0, nsub = 0;
+  float ctrl = 0.f;
+  if (reset_now) {
+    do_reset(P, d, e, lane, s, tg, task);
+  } else {
+    load_state(d, e, lane, s);
+    tg.x = d.target[0 * N + e]; tg.y = d.target[1 * N + e]; tg.qw = d.target[2 * N + e]; tg.qz = d.target[3 * N + e];
+    if (a.mode == JB_MODE_STEP) { ctrl = a.actions[e]; nsub = d.n_sub; }
+  }
+  if (nsub == 0) {
+    // reset / contact report: one forward-only pass (mj_forward) for the warm start / the contact list
+    QReport<float> rep = {a.rep_geom + (size_t)e * 4 * JBQ_CAP, a.rep_dist + (size_t)e * 4 * JBQ_CAP, 1};
+    if (a.mode == JB_MODE_CONTACTS) {
+#pragma unroll
+      for (int i = 0; i < JBQ_CAP; i++) rep.geom[lane * JBQ_CAP + i] = -1;
+    }
+    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, true, &iters, &ncon_sum, &overflow,
+                                    a.mode == JB_MODE_CONTACTS ? &rep : nullptr);
+    if (a.mode == JB_MODE_CONTACTS) return;
+    store_state(d, e, lane, s);
+    if (lane == 0) {
+      write_obs(P, d, e, s, task, tg, a.obs, nullptr);
+      if (a.reward) a.reward[e] = 0.f;
+      if (a.step_type) a.step_type[e] = JB_STEP_FIRST;
+    }
+    return;
+  }
+  for (int k = 0; k < nsub; k++)
+    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, false, &iters, &ncon_sum, &overflow, nullptr);
+  {   // mj_step1 of the last sub-step normalises qpos quaternions in place
+    float qn = rsqrtf(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
+    s.quat[0] *= qn; s.quat[1] *= qn; s.quat[2] *= qn; s.quat[3] *= qn;
+  }
+  // mj_checkPos / mj_checkVel: MuJoCo resets the data (dm_control raises PhysicsError); here the env restarts
+  int bad = cm.isum(state_bad(s) ? 1 : 0);
+  if (bad) do_reset(P, d, e, lane, s, tg, task);
+  store_state(d, e, lane, s);
+  if (lane == 0) {
+    int sc = bad ? 0 : d.step_count[e] + 1;
+    d.step_count[e] = sc;
+    int st = JB_STEP_MID;
+    if (d.step_limit > 0 && sc >= d.step_limit) { st = JB_STEP_LAST; d.reset_next[e] = 1; }
+    write_obs(P, d, e, s, task, tg, a.obs, a.reward);
+    if (a.step_type) a.step_type[e] = st;
+    atomicAdd(&d.counters[1], (unsigned long long)iters);
+    atomicAdd(&d.counters[2], (unsigned long long)ncon_sum);
+    if (overflow) atomicAdd(&d.counters[3], (unsigned long long)overflow);
+    if (bad) atomicAdd(&d.counters[4], 1ull);
+    if (e == 0) atomicAdd(&d.counters[0], (unsigned long long)d.n_sub * (unsigned long long)N);
+  }
+}
+
+cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st) {
+  const size_t smem = (d.per_env ? JB_ENVS_PER_BLOCK * JBP_SIZE : JBP_SIZE) * sizeof(float);
+  const int blocks = (d.N + JB_ENVS_PER_BLOCK - 1) / JB_ENVS_PER_BLOCK;
+  jb_sim_kernel<<<blocks, JB_BLOCK, smem, st>>>(d, a);
+  return cudaGetLastError();
+}
+
+cudaError_t jb_configure_kernels(void) {
+  return cudaFuncSetAttribute(jb_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)(JB_ENVS_PER_BLOCK * JBP_SIZE * sizeof(float)));
+}

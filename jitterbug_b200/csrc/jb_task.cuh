@@ -9,7 +9,8 @@
 #ifndef JB_TASK_CUH
 #define JB_TASK_CUH
 
-#include "jb_dynamics.cuh"
+#include "jb_math.cuh"
+#include "jb_packed.h"
 #include <stdint.h>
 
 #define JB_PI 3.14159265358979323846
@@ -48,8 +49,9 @@ template <typename T> JB_HD T jb_tol_gauss(T dist_to_bound, T margin) {
 template <typename T> struct JbTarget { T x, y, qw, qz; };
 
 // Observation (normalised, OrderedDict order) + reward for one env.  Returns the observation length.
-template <typename T, typename M>
-JB_HD int jb_obs_reward(const M& m, const JbState<T>& s, int task, const JbTarget<T>& tg, T* obs, T* reward) {
+// `s` is any state with fields pos[3], quat[4], vlin[3], w[3], qm, vm; `g` the packed model (jb_packed.h).
+template <typename T, typename S>
+JB_HD int jb_obs_reward(const T* g, const S& s, int task, const JbTarget<T>& tg, T* obs, T* reward) {
   T R[9];
   quat2mat(R, s.quat);
   T jyaw = jb_atan2(R[3], R[0]) - (T)(JB_PI / 2);
@@ -58,12 +60,11 @@ JB_HD int jb_obs_reward(const M& m, const JbState<T>& s, int task, const JbTarge
   T tyaw = jb_atan2(ts, tc);
   T angle = jb_wrap_pi(tyaw - jyaw);
   T motor = jb_wrap_pi(s.qm + (T)(JB_PI / 2));
-  T rel[3] = {tg.x - s.pos[0], tg.y - s.pos[1], (T)m.target_pos0[2] - s.pos[2]};
+  T rel[3] = {tg.x - s.pos[0], tg.y - s.pos[1], g[G_TGT0 + 2] - s.pos[2]};
   T tib[3];
   mulMTV(tib, R, rel);
   // framelinvel sensor: world velocity of the root body's own COM = v + R (w x c0)
-  T c0[3], wc[3], sv[3];
-  ld3(c0, m.c0);
+  T c0[3] = {g[G_C0], g[G_C0 + 1], g[G_C0 + 2]}, wc[3], sv[3];
   cross3(wc, s.w, c0);
   mulMV(sv, R, wc);
   sv[0] += s.vlin[0]; sv[1] += s.vlin[1]; sv[2] += s.vlin[2];
@@ -131,8 +132,9 @@ JB_HD JbPhilox jb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 JB_HD float jb_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }   // [0, 1)
 
 // Episode initial conditions (jitterbug.py:601-666): returns the reset state and target for (global env id, episode)
-template <typename T, typename M>
-JB_HD void jb_reset_env(const M& m, JbState<T>& s, JbTarget<T>& tg, int task, int random_pose,
+// Fills the root part of the state (pos, quat, zero velocities / motor / warm start); the caller zeroes its leg state.
+template <typename T, typename S>
+JB_HD void jb_reset_env(const T* g, S& s, JbTarget<T>& tg, int task, int random_pose,
                         uint64_t seed, uint32_t env_gid, uint32_t episode) {
   JbPhilox r0 = jb_philox(env_gid, episode, 0u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
   JbPhilox r1 = jb_philox(env_gid, episode, 1u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -142,7 +144,7 @@ JB_HD void jb_reset_env(const M& m, JbState<T>& s, JbTarget<T>& tg, int task, in
   T rot = (T)(2 * JB_PI) * (T)jb_u01(r0.v[3]);                   // np.random.random() * 2*pi
   T ax = (T)0.05 * (T)jb_u01(r1.v[0]) - (T)0.025;                // np.random.random(2) * .05 - .025
   T ay = (T)0.05 * (T)jb_u01(r1.v[1]) - (T)0.025;
-  tg.x = (T)m.target_pos0[0]; tg.y = (T)m.target_pos0[1]; tg.qw = (T)1; tg.qz = (T)0;
+  tg.x = g[G_TGT0]; tg.y = g[G_TGT0 + 1]; tg.qw = (T)1; tg.qz = (T)0;
   T sa, ca;
   if (task == JB_TASK_MOVE_TO_POSITION || task == JB_TASK_MOVE_TO_POSE) {
     jb_sincos(angle, &sa, &ca);
@@ -152,20 +154,16 @@ JB_HD void jb_reset_env(const M& m, JbState<T>& s, JbTarget<T>& tg, int task, in
     jb_sincos((T)0.5 * yaw, &sa, &ca);
     tg.qw = ca; tg.qz = sa;
   }
-  s.pos[0] = (T)m.root_pos0[0]; s.pos[1] = (T)m.root_pos0[1]; s.pos[2] = (T)m.root_pos0[2];
+  s.pos[0] = g[G_ROOTPOS0]; s.pos[1] = g[G_ROOTPOS0 + 1]; s.pos[2] = g[G_ROOTPOS0 + 2];
   s.quat[0] = 1; s.quat[1] = 0; s.quat[2] = 0; s.quat[3] = 0;
   if (random_pose) {
     T nrm = (T)1 / jb_sqrt(ax * ax + ay * ay + (T)1);
     jb_sincos((T)0.5 * rot, &sa, &ca);
     s.quat[0] = ca; s.quat[1] = sa * ax * nrm; s.quat[2] = sa * ay * nrm; s.quat[3] = sa * nrm;
   }
-#pragma unroll
-  for (int k = 0; k < JB_NLEG; k++) { s.ql[k][0] = 0; s.ql[k][1] = 0; s.vl[k][0] = 0; s.vl[k][1] = 0; }
   s.qm = 0; s.vm = 0; s.rev = 0;
 #pragma unroll
   for (int i = 0; i < 3; i++) { s.vlin[i] = 0; s.w[i] = 0; }
-#pragma unroll
-  for (int i = 0; i < JB_NV; i++) s.warm[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------ heuristic policies

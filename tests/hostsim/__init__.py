@@ -10,7 +10,7 @@ from jitterbug_b200 import model as jbmodel
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libhostsim.so")
 _SRC = [os.path.join(_HERE, "hostsim.cpp"),
-        os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", "jb_dynamics.cuh"),
+        os.path.join(_HERE, "ref_thread_per_env.cuh"),
         os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", "jb_model.h")]
 
 
@@ -53,3 +53,50 @@ def substeps(model_struct, qpos, qvel, warm, ctrl, nsub=1, double=True, want_dia
     it = fn(C.byref(model_struct), q.ctypes.data_as(C.POINTER(real)), v.ctypes.data_as(C.POINTER(real)),
             w.ctypes.data_as(C.POINTER(real)), real(ctrl), C.c_int(nsub), C.byref(diag) if want_diag else None)
     return q, v, w, it, diag
+
+
+# ------------------------------------------------------------------------------------------------ quad emulation
+_QSO = os.path.join(_HERE, "libquadsim.so")
+_QSRC = [os.path.join(_HERE, "quadsim.cpp")] + [os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", f)
+                                                 for f in ("jb_quad.cuh", "jb_math.cuh", "jb_packed.h", "jb_model.h")]
+_qlib = None
+
+
+def qlib():
+    global _qlib
+    if _qlib is None:
+        if not os.path.exists(_QSO) or os.path.getmtime(_QSO) < max(os.path.getmtime(s) for s in _QSRC):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++14", "-ffp-contract=off",
+                                   "-o", _QSO, _QSRC[0]])
+        _qlib = C.CDLL(_QSO)
+    return _qlib
+
+
+def pack(model_struct, double=True):
+    L = qlib()
+    n = L.hq_packed_size()
+    out = np.zeros(n, dtype=np.float64 if double else np.float32)
+    (L.hq_pack_f64 if double else L.hq_pack_f32)(C.byref(model_struct), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def quad_substeps(packed, qpos, qvel, warm, ctrl, nsub=1, forward_only=False, want_contacts=False):
+    """Advance one env with the fiber-emulated quad kernel.  Returns (qpos, qvel, warm, iters, ncon, contacts, overflow)."""
+    L = qlib()
+    double = packed.dtype == np.float64
+    dt = packed.dtype
+    real = C.c_double if double else C.c_float
+    q = np.array(qpos, dtype=dt).copy(); v = np.array(qvel, dtype=dt).copy(); w = np.array(warm, dtype=dt).copy()
+    ncon, ovf = C.c_int(), C.c_int()
+    geom = np.full(32, -1, dtype=np.int32); dist = np.zeros(32, dtype=dt)
+    fn = L.hq_substeps_f64 if double else L.hq_substeps_f32
+    fn.restype = C.c_int
+    P = C.c_void_p
+    it = fn(packed.ctypes.data_as(P), q.ctypes.data_as(P), v.ctypes.data_as(P), w.ctypes.data_as(P), real(ctrl),
+            C.c_int(nsub), C.c_int(int(forward_only)), C.byref(ncon),
+            geom.ctypes.data_as(P) if want_contacts else None, dist.ctypes.data_as(P) if want_contacts else None,
+            C.byref(ovf))
+    if it < 0:
+        raise RuntimeError("replicated quad state diverged between lanes")
+    cons = sorted((int(g), float(d)) for g, d in zip(geom, dist) if g >= 0) if want_contacts else None
+    return q, v, w, it, ncon.value, cons, ovf.value

@@ -27,7 +27,7 @@ inline Cnt& operator*=(Cnt& a, Cnt b) { g_flops++; a.v *= b.v; return a; }
 inline Cnt jb_sqrt(Cnt x) { g_flops++; return Cnt(sqrt(x.v)); }
 inline Cnt jb_abs(Cnt x) { g_flops++; return Cnt(fabs(x.v)); }
 inline void jb_sincos(Cnt x, Cnt* s, Cnt* c) { g_flops += 2; *s = Cnt(sin(x.v)); *c = Cnt(cos(x.v)); }
-#include "../../jitterbug_b200/csrc/jb_dynamics.cuh"
+#include "ref_thread_per_env.cuh"
 template <> struct JbEps<Cnt> {
   static Cnt newton_tol() { return Cnt(2e-6); }
   static Cnt ls_tol() { return Cnt(1e-5); }

@@ -1,7 +1,7 @@
 // TEST-ONLY host instantiation of the GPU sub-step algorithm (jitterbug_b200/csrc/jb_dynamics.cuh) in fp64 and fp32.
 // It lets the CPU test-suite compare the *algorithm* the CUDA kernel runs against the oracle without a GPU and
 // separates algorithmic parity (fp64, ~1e-10) from fp32 rounding.  Never loaded by the product package.
-#include "../../jitterbug_b200/csrc/jb_dynamics.cuh"
+#include "ref_thread_per_env.cuh"
 #include <string.h>
 
 struct JbGeomD { JB_GEOM_FIELDS(double) };
