@@ -12,7 +12,7 @@ import os
 from .model import JbModelF
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libjbsim.so")
+LIB_PATH = os.environ.get("JB_LIB", os.path.join(_HERE, "_lib", "libjbsim.so"))   # JB_LIB: tuning variants
 
 
 class JbSimConfig(C.Structure):

@@ -16,8 +16,11 @@ CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
 UNITS = ["jb_sim_kernel.cu", "jb_api.cu"]
+# -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
+# 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + \
+    os.environ.get("JB_NVCC_EXTRA", "").split()
 
 
 def _sources():

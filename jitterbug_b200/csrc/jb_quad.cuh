@@ -18,6 +18,14 @@
 #include "jb_packed.h"
 #include <stdint.h>
 
+// cold paths (contact creation, cylinder / box / ellipsoid narrow phase) are real function calls on the device: they
+// run rarely and inlining them at every call site made the kernel several times larger than the instruction cache
+#if defined(__CUDACC__)
+#define JB_COLD __host__ __device__ __noinline__
+#else
+#define JB_COLD inline
+#endif
+
 #define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms) */
 #define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
@@ -186,8 +194,9 @@ template <typename T> JB_HD T jbq_impedance(const T* si, T dist) {
   else if (power <= (T)1) y = x;
   else {
 #if defined(__CUDA_ARCH__)
-    y = x <= mid ? (T)(powf((float)x, (float)power) / powf((float)mid, (float)power - 1.f))
-                 : (T)(1.f - powf(1.f - (float)x, (float)power) / powf(1.f - (float)mid, (float)power - 1.f));
+    // non-default solimp power: fast intrinsics keep this cold path small (the Jitterbug models use power = 2)
+    y = x <= mid ? (T)(__powf((float)x, (float)power) / __powf((float)mid, (float)power - 1.f))
+                 : (T)(1.f - __powf(1.f - (float)x, (float)power) / __powf(1.f - (float)mid, (float)power - 1.f));
 #else
     y = x <= mid ? (T)(pow((double)x, (double)power) / pow((double)mid, (double)power - 1))
                  : (T)(1 - pow(1 - (double)x, (double)power) / pow(1 - (double)mid, (double)power - 1));
@@ -207,7 +216,7 @@ template <typename T> struct QBody {     // how a geom's body moves: joint colum
 };
 
 template <typename T>
-JB_HD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
+JB_COLD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
                     const QReport<T>* rep, int lane) {
   if (!(dist < (T)0)) return;            // dist >= includemargin (= 0): MuJoCo excludes it from the solver
   int i = cs.n;
@@ -250,7 +259,7 @@ JB_HD void jbq_col_sphere(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const
 
 // mjc_PlaneCylinder; xax is only needed when the axis is exactly parallel to the floor normal
 template <typename T>
-JB_HD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+JB_COLD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
                             const T* ax_in, const T* xax, T r, T hl, const QReport<T>* rep, int lane) {
   T dist0 = fr.pz + dot3(fr.n, c);
   T ax[3] = {ax_in[0], ax_in[1], ax_in[2]};
@@ -297,7 +306,7 @@ JB_HD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, con
 }
 
 template <typename T>
-JB_HD void jbq_col_box(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c, const T* Rg,
+JB_COLD void jbq_col_box(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c, const T* Rg,
                        const T* half, const QReport<T>* rep, int lane) {
   T dist = fr.pz + dot3(fr.n, c);
   int cnt = 0;
@@ -316,7 +325,7 @@ JB_HD void jbq_col_box(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QB
 }
 
 template <typename T>
-JB_HD void jbq_col_ellipsoid(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+JB_COLD void jbq_col_ellipsoid(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
                              const T* Rg, const T* size, const QReport<T>* rep, int lane) {
   T dir[3] = {-fr.n[0], -fr.n[1], -fr.n[2]}, loc[3];
   mulMTV(loc, Rg, dir);
@@ -741,11 +750,14 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 
   const int ncon = cm.isum(cs.n);
 
-  // ---------------- constraint solve (primal Newton)
+  // ---------------- constraint solve (primal Newton).  Control flow is kept WARP-uniform (Comm::warp_any): every quad
+  // of the warp runs the same number of Newton / line-search iterations, quads that are finished take zero-length
+  // steps.  That is what SIMT divergence would cost anyway, and it lets every quad shuffle run with the full mask.
   QVec<T> a = as_;
   int iters = 0;
   const T mu = g[G_FRIC];
-  if (ncon > 0) {
+  const bool has_con = ncon > 0;
+  if (cm.warp_any(has_con)) {
     QVec<T> aw;
     {
       T lw[3] = {s.wr[0], s.wr[1], s.wr[2]}, lr[3];
@@ -764,14 +776,14 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     T csm = jbq_cost(cs, mu);
     cm.sum2(cw, csm);
     cw += (T)0.5 * qv_dot_rep(res, da);
-    if (cw > csm) {
+    if (cw > csm || !has_con) {
       a = as_; Ma = fs;                 // M a_s = f_s ; ww already evaluated at a_s
     } else {
       a = aw;
       jbq_eval_ww(cs, fr.Rw, a);
     }
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
-    T f7[7], fla, flb;
+    T f7[8], fla, flb;
     uint32_t mask = jbq_forces(cs, fr.Rw, mu, f7, &fla, &flb);
     cm.sumN(f7, 7);
     QVec<T> grad = Ma;
@@ -780,7 +792,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     for (int i = 0; i < 6; i++) grad.r[i] -= f7[i];
     grad.la -= fla; grad.lb -= flb; grad.mo -= f7[6];
     const int maxit = JbEps<T>::newton_iters();
-    while (iters < maxit) {
+    bool done = !has_con;
+    while (cm.warp_any(!done)) {
       QArrow<T> H = Mx;
       T part[28];
       jbq_hessian(H, part, cs, fr.Rw, mu);
@@ -804,27 +817,37 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       uint32_t m1 = jbq_ls_local(cs, mu, (T)1, &red[3], &red[4]);
       red[5] = m1 == mask ? (T)0 : (T)1;
       cm.sumN(red, 6);
-      T g1 = red[0] + qv_dot_rep(search, res), g2 = red[1] + qv_dot_rep(search, Mv), d0 = red[2] + qv_dot_rep(search, grad);
-      if (!(d0 < (T)0)) break;                           // not a descent direction: converged to rounding
+      const T g1 = red[0] + qv_dot_rep(search, res), g2 = red[1] + qv_dot_rep(search, Mv);
+      const T d0 = red[2] + qv_dot_rep(search, grad);
+      const bool descent = d0 < (T)0;                    // otherwise: converged to rounding
+      const bool full = red[5] == (T)0;                  // same active set at alpha = 1: the Newton step is exact
       T alpha = 1;
-      bool full = red[5] == (T)0;                        // same active set at alpha = 1: the Newton step is exact
-      if (!full) {
+      {
+        // exact line search on the piecewise-quadratic 1-D cost: safeguarded Newton on phi'
         T d = g1 + g2 + red[3], dd = g2 + red[4];
-        T lo = 0, hi = -1, tol = JbEps<T>::ls_tol() * jb_abs(d0);
-        for (int it = 0; it < 30; it++) {
-          if (jb_abs(d) <= tol) break;
-          if (d < (T)0) lo = alpha; else hi = alpha;
-          T an = alpha - d / dd;
-          if (hi > (T)0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
-          else if (!(an > lo)) an = alpha * (T)2;
-          if (an == alpha) break;
-          alpha = an;
+        T lo = 0, hi = -1;
+        const T tol = JbEps<T>::ls_tol() * jb_abs(d0);
+        bool searching = !done && descent && !full && jb_abs(d) > tol;
+        for (int it = 0; it < 30 && cm.warp_any(searching); it++) {
+          T an = alpha;
+          if (searching) {
+            if (d < (T)0) lo = alpha; else hi = alpha;
+            an = alpha - d / dd;
+            if (hi > (T)0 && !(an > lo && an < hi)) an = (T)0.5 * (lo + hi);
+            else if (!(an > lo)) an = alpha * (T)2;
+            if (an == alpha) searching = false;
+          }
           T dl, hl;
-          jbq_ls_local(cs, mu, alpha, &dl, &hl);
+          jbq_ls_local(cs, mu, an, &dl, &hl);
           cm.sum2(dl, hl);
-          d = g1 + alpha * g2 + dl; dd = g2 + hl;
+          if (searching) {
+            alpha = an;
+            d = g1 + alpha * g2 + dl; dd = g2 + hl;
+            if (jb_abs(d) <= tol) searching = false;
+          }
         }
       }
+      if (done || !descent) alpha = 0;
       qv_axpy(a, alpha, search);
       qv_axpy(Ma, alpha, Mv);
       for (int i = 0; i < cs.n; i++) {
@@ -841,11 +864,13 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #pragma unroll
       for (int i = 0; i < 6; i++) grad.r[i] -= f8[i];
       grad.la -= fla; grad.lb -= flb; grad.mo -= f8[6];
-      iters++;
       T gl = qv_dot_leg(grad, grad);
       gl = cm.sum(gl);
-      T gn = scale * jb_sqrt(gl + qv_dot_rep(grad, grad));
-      if ((full && f8[7] == (T)0) || gn < JbEps<T>::newton_tol()) break;
+      const T gn = scale * jb_sqrt(gl + qv_dot_rep(grad, grad));
+      if (!done) {
+        if (descent) iters++;
+        if (!descent || (full && f8[7] == (T)0) || gn < JbEps<T>::newton_tol() || iters >= maxit) done = true;
+      }
     }
   }
   if (iter_accum) *iter_accum += iters;

@@ -6,11 +6,19 @@
 #include "jb_quad.cuh"
 #include "jb_task.cuh"
 
+#ifndef JB_SYNC_SUBSTEP
+#define JB_SYNC_SUBSTEP 1
+#endif
+#ifndef JB_MIN_BLOCKS
+#define JB_MIN_BLOCKS 2
+#endif
+
+// Quad sums as xor-butterflies over lanes {l, l^1, l^2, l^3}.  The kernel keeps control flow warp-uniform around every
+// call (see jb_quad.cuh), so all 32 lanes execute each shuffle together and the full mask is legal.
 struct QuadCommGPU {
-  unsigned mask;
   __device__ __forceinline__ float sum(float v) {
-    v += __shfl_xor_sync(mask, v, 1);
-    v += __shfl_xor_sync(mask, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   }
   __device__ __forceinline__ void sum2(float& a, float& b) { a = sum(a); b = sum(b); }
@@ -19,10 +27,11 @@ struct QuadCommGPU {
     for (int i = 0; i < 28; i++) if (i < n) v[i] = sum(v[i]);
   }
   __device__ __forceinline__ int isum(int v) {
-    v += __shfl_xor_sync(mask, v, 1);
-    v += __shfl_xor_sync(mask, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   }
+  __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
 };
 
 __device__ __forceinline__ void load_state(const JbDev& d, int e, int lane, QState<float>& s) {
@@ -74,15 +83,15 @@ __device__ __forceinline__ bool state_bad(const QState<float>& s) {
 }
 
 __device__ __forceinline__ void do_reset(const float* g, const JbDev& d, int e, int lane, QState<float>& s,
-                                         JbTarget<float>& tg, int task) {
+                                         JbTarget<float>& tg, int task, bool live) {
   int ep = d.episode[e];
   jb_reset_env<float>(g, s, tg, task, d.random_pose, d.seed, d.env_id_offset + (unsigned)e, (unsigned)ep);
   s.qa = s.qb = s.va = s.vb = 0.f;
 #pragma unroll
   for (int i = 0; i < 6; i++) s.wr[i] = 0.f;
   s.wla = s.wlb = s.wmo = 0.f;
-  __syncwarp(0xFu << (threadIdx.x & 28));       // all four lanes have read episode[e] before lane 0 bumps it
-  if (lane == 0) {
+  __syncwarp(__activemask());                   // all four lanes have read episode[e] before lane 0 bumps it
+  if (lane == 0 && live) {
     d.episode[e] = ep + 1;
     d.step_count[e] = 0;
     d.reset_next[e] = 0;
@@ -106,11 +115,11 @@ __device__ __forceinline__ void write_obs(const float* g, const JbDev& d, int e,
 
 extern __shared__ float jb_smem[];
 
-__global__ void __launch_bounds__(JB_BLOCK)
+__global__ void __launch_bounds__(JB_BLOCK, JB_MIN_BLOCKS)
 jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 3;
-  const int e = blockIdx.x * JB_ENVS_PER_BLOCK + (tid >> 2);
+  const int e_raw = blockIdx.x * JB_ENVS_PER_BLOCK + (tid >> 2);
   // ---- packed model -> shared memory
   if (d.per_env) {
     const int e0 = blockIdx.x * JB_ENVS_PER_BLOCK;
@@ -121,52 +130,66 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
     for (int i = tid; i < JBP_SIZE; i += JB_BLOCK) jb_smem[i] = d.packed[i];
   }
   __syncthreads();
-  if (e >= d.N) return;
+  // Every thread of the CTA runs the whole kernel body (the quad shuffles and warp votes need full warps): padding
+  // quads past the end of the batch and envs not selected by a reset mask shadow a valid env and skip all stores.
+  const int e = min(e_raw, d.N - 1);
   const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_SIZE : jb_smem;
   QuadCommGPU cm;
-  cm.mask = 0xFu << ((tid & 31) & 28);
   const int N = d.N;
   const int task = d.task[e];
   QState<float> s;
   JbTarget<float> tg;
   const bool reset_now = a.mode == JB_MODE_RESET ? (!a.mask || a.mask[e]) : (a.mode == JB_MODE_STEP && d.reset_next[e]);
-  if (a.mode == JB_MODE_RESET && !reset_now) return;
+  const bool live = e_raw < d.N && !(a.mode == JB_MODE_RESET && !reset_now);
   int iters = 0, ncon_sum = 0, overflow = 0, nsub = 0;
   float ctrl = 0.f;
   if (reset_now) {
-    do_reset(P, d, e, lane, s, tg, task);
+    do_reset(P, d, e, lane, s, tg, task, live);
   } else {
     load_state(d, e, lane, s);
     tg.x = d.target[0 * N + e]; tg.y = d.target[1 * N + e]; tg.qw = d.target[2 * N + e]; tg.qz = d.target[3 * N + e];
     if (a.mode == JB_MODE_STEP) { ctrl = a.actions[e]; nsub = d.n_sub; }
   }
-  if (nsub == 0) {
-    // reset / contact report: one forward-only pass (mj_forward) for the warm start / the contact list
-    QReport<float> rep = {a.rep_geom + (size_t)e * 4 * JBQ_CAP, a.rep_dist + (size_t)e * 4 * JBQ_CAP, 1};
-    if (a.mode == JB_MODE_CONTACTS) {
+  // a reset / contact report runs one forward-only pass (mj_forward) for the warm start / the contact list.
+  // Envs of one warp can be in different modes only at episode boundaries; the trip count is made warp-uniform.
+  const bool fwd_only = nsub == 0;
+  QReport<float> rep = {a.rep_geom + (size_t)e * 4 * JBQ_CAP, a.rep_dist + (size_t)e * 4 * JBQ_CAP, 1};
+  const bool want_rep = a.mode == JB_MODE_CONTACTS && live;
+  if (want_rep) {
 #pragma unroll
-      for (int i = 0; i < JBQ_CAP; i++) rep.geom[lane * JBQ_CAP + i] = -1;
-    }
-    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, true, &iters, &ncon_sum, &overflow,
-                                    a.mode == JB_MODE_CONTACTS ? &rep : nullptr);
-    if (a.mode == JB_MODE_CONTACTS) return;
-    store_state(d, e, lane, s);
-    if (lane == 0) {
-      write_obs(P, d, e, s, task, tg, a.obs, nullptr);
-      if (a.reward) a.reward[e] = 0.f;
-      if (a.step_type) a.step_type[e] = JB_STEP_FIRST;
+    for (int i = 0; i < JBQ_CAP; i++) rep.geom[lane * JBQ_CAP + i] = -1;
+  }
+  int trips = fwd_only ? 1 : nsub;
+  trips = __reduce_max_sync(0xffffffffu, trips);
+  for (int k = 0; k < trips; k++) {
+#if JB_SYNC_SUBSTEP
+    __syncthreads();            // keeps the CTA's warps in the same code region: instruction-cache lines are shared
+#endif
+    const bool on = fwd_only ? k == 0 : k < nsub;
+    QState<float> keep = s;
+    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, fwd_only, &iters, &ncon_sum, &overflow, want_rep ? &rep : nullptr);
+    if (!on) s = keep;          // warp-mates with fewer trips idle (never happens in a lock-stepped batch)
+  }
+  if (a.mode == JB_MODE_CONTACTS) return;
+  if (fwd_only) {
+    if (live) {
+      store_state(d, e, lane, s);
+      if (lane == 0) {
+        write_obs(P, d, e, s, task, tg, a.obs, nullptr);
+        if (a.reward) a.reward[e] = 0.f;
+        if (a.step_type) a.step_type[e] = JB_STEP_FIRST;
+      }
     }
     return;
   }
-  for (int k = 0; k < nsub; k++)
-    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, false, &iters, &ncon_sum, &overflow, nullptr);
   {   // mj_step1 of the last sub-step normalises qpos quaternions in place
     float qn = rsqrtf(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
     s.quat[0] *= qn; s.quat[1] *= qn; s.quat[2] *= qn; s.quat[3] *= qn;
   }
   // mj_checkPos / mj_checkVel: MuJoCo resets the data (dm_control raises PhysicsError); here the env restarts
-  int bad = cm.isum(state_bad(s) ? 1 : 0);
-  if (bad) do_reset(P, d, e, lane, s, tg, task);
+  const int bad = cm.isum(state_bad(s) ? 1 : 0);
+  if (bad) do_reset(P, d, e, lane, s, tg, task, live);
+  if (!live) return;
   store_state(d, e, lane, s);
   if (lane == 0) {
     int sc = bad ? 0 : d.step_count[e] + 1;

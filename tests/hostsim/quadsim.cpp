@@ -39,6 +39,7 @@ template <typename T> struct FiberComm {
   void sum2(T& a, T& b) { T v[2] = {a, b}; exchange(v, 2); a = v[0]; b = v[1]; }
   void sumN(T* v, int n) { exchange(v, n); }
   int isum(int v) { T x = (T)v; exchange(&x, 1); return (int)(x + (T)0.5); }
+  bool warp_any(bool p) { return isum(p ? 1 : 0) > 0; }   // the emulated "warp" is one quad
 };
 
 template <typename T> struct Job {
