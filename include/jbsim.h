@@ -83,6 +83,11 @@ int jb_sim_get_contacts(JbSim* sim, int32_t* ncon_dev, int32_t* geom_dev, float*
  * [3] contact-slot overflows, [4] diverged-state resets.  Synchronises the device. */
 int jb_sim_get_counters(JbSim* sim, unsigned long long* out5_host);
 
+/* Profiling builds only (-DJBQ_PHASE_TIMERS): clock64 cycles summed over warps for the 7 phases of the sub-step
+ * ([1] leg kinematics+collision, [2] root/rotor, [3] extra geoms, [4] factor M + smooth solve, [5] warm-start
+ * selection, [6] Newton loop, [7] Euler); zeros otherwise.  Synchronises the device. */
+int jb_sim_get_phase_cycles(JbSim* sim, unsigned long long* out8_host);
+
 /* FP32 FMA-pipe peak of `device` in TFLOP/s (FFMA-chain microbenchmark): the roofline denominator of this
  * compute-bound path.  Synchronises the device. */
 int jb_measure_fp32_peak(int device, double* tflops_out);

@@ -38,6 +38,7 @@ SYMBOLS = {
     "jb_sim_set_step_count": (C.c_int, [_P, _P, _P]),
     "jb_sim_get_contacts": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
     "jb_sim_get_counters": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
+    "jb_sim_get_phase_cycles": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "jb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "jb_sim_num_envs": (C.c_int, [_P]),
     "jb_sim_obs_stride": (C.c_int, [_P]),

@@ -240,5 +240,11 @@ class BatchedJitterbugEnv:
         keys = ("substeps", "newton_iterations", "contacts", "contact_overflows", "diverged_resets")
         return dict(zip(keys, [int(x) for x in out]))
 
+    def phase_cycles(self):
+        """Per-phase clock64 sums (profiling builds with -DJBQ_PHASE_TIMERS only; zeros otherwise)."""
+        out = (C.c_ulonglong * 8)()
+        _native.check(self._lib.jb_sim_get_phase_cycles(self._h, out))
+        return [int(x) for x in out]
+
     def observation_layout(self, task: Optional[str] = None):
         return observation_layout(task or self.task or self.task_names[0])

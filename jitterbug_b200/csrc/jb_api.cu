@@ -155,7 +155,7 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   CUDA_TRY(cudaMalloc(&d.step_count, N * sizeof(int)));
   CUDA_TRY(cudaMalloc(&d.episode, N * sizeof(int)));
   CUDA_TRY(cudaMalloc(&d.reset_next, N));
-  CUDA_TRY(cudaMalloc(&d.counters, 5 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&d.counters, 16 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemset(d.qpos, 0, 16 * N * sizeof(float)));
   CUDA_TRY(cudaMemset(d.qvel, 0, 15 * N * sizeof(float)));
   CUDA_TRY(cudaMemset(d.warm, 0, 15 * N * sizeof(float)));
@@ -164,7 +164,7 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   CUDA_TRY(cudaMemset(d.step_count, 0, N * sizeof(int)));
   CUDA_TRY(cudaMemset(d.episode, 0, N * sizeof(int)));
   CUDA_TRY(cudaMemset(d.reset_next, 1, N));           // a step() before any reset() is a reset (dm_control)
-  CUDA_TRY(cudaMemset(d.counters, 0, 5 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d.counters, 0, 16 * sizeof(unsigned long long)));
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
   {
@@ -295,6 +295,14 @@ int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* d
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+// profiling builds (-DJBQ_PHASE_TIMERS): per-phase clock64 sums of lane 0 of every warp, slots 9..15
+int jb_sim_get_phase_cycles(JbSim* s, unsigned long long* out8_host) {
+  if (!s || !out8_host) return fail("jb_sim_get_phase_cycles: null argument");
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out8_host, s->d.counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int jb_sim_get_counters(JbSim* s, unsigned long long* out5_host) {
   if (!s || !out5_host) return fail("jb_sim_get_counters: null argument");
   CUDA_TRY(cudaDeviceSynchronize());

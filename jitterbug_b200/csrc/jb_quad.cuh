@@ -26,6 +26,15 @@
 #define JB_COLD inline
 #endif
 
+// optional in-kernel phase timers (profiling builds only): Comm::tick(phase) closes the interval that ends here
+#ifdef JBQ_PHASE_TIMERS
+#define JBQ_TICK(p) do { cm.phase_sync(p); cm.tick(p); } while (0)
+#else
+#define JBQ_TICK(p) cm.phase_sync(p)
+#endif
+#ifdef JBQ_DEBUG_COUNT
+static long long g_jbq_ls_iters = 0, g_jbq_newton_trips = 0;
+#endif
 #define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms) */
 #define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
@@ -469,12 +478,15 @@ template <typename T> JB_HD uint32_t jbq_ls_local(const QConSet<T>& cs, T mu, T 
 template <typename T, typename Comm>
 JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, bool forward_only, int* iter_accum,
                        int* ncon_accum, int* overflow_accum, const QReport<T>* rep) {
+  // forward_only (mj_forward: everything up to qacc / qacc_warmstart) is a sub-step of length zero, so that every
+  // thread of a CTA follows the same control flow whatever its env is doing (the phase barriers below rely on it)
   const T* g = P;
   const T* X = P + JBP_X + lane;
   const T* L = P + JBP_L + lane;
 #define LX(i) X[4 * (i)]
 #define LL(i) L[4 * (i)]
-  const T h = g[G_H];
+  const T h = forward_only ? (T)0 : g[G_H];
+  JBQ_TICK(0);
   // ---------------- root frame (replicated)
   QFrame<T> fr;
   {
@@ -614,7 +626,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           jbq_col_cylinder<T>(g, cs, fr, bl, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
         }
       }
-      // knee sphere (upper body)
+        // knee sphere (upper body)
       gh[0] = LL(L_KN_C); gh[1] = LL(L_KN_C + 1); gh[2] = LL(L_KN_C + 2);
       sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
       jbq_col_sphere<T>(g, cs, fr, bu, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane);
@@ -632,6 +644,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     }
   }
 
+  JBQ_TICK(1);
   // ---------------- quad-sum the leg partials: first moment (3), origin inertia (6), bias force/torque (6)
   {
     T red[15] = {ht[0], ht[1], ht[2], It[0], It[1], It[2], It[3], It[4], It[5], bF[0], bF[1], bF[2], bT[0], bT[1], bT[2]};
@@ -699,6 +712,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     Mx.R[JBQ_TRI(4, 3)] = It[3]; Mx.R[JBQ_TRI(5, 3)] = It[4]; Mx.R[JBQ_TRI(5, 4)] = It[5];
   }
 
+  JBQ_TICK(2);
   // ---------------- collision of the extra geoms: lanes 0,1 -> core boxes; lane 2 -> root cylinder + ellipsoid;
   //                  lane 3 -> rotor cylinder + ellipsoid
   if (lane < 2) {
@@ -740,6 +754,11 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     }
   }
 
+#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 1      /* timing experiments only: kinematics + collision */
+  s.wla += Mx.aa + Mx.R[3] + bias.r[0] + (T)cs.n;
+  return;
+#endif
+  JBQ_TICK(3);
   // ---------------- smooth dynamics: f_s = passive + actuator - bias ; a_s = M^-1 f_s
   QVec<T> fs = fpass;
   qv_axpy(fs, (T)-1, bias);
@@ -748,6 +767,11 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   qarrow_factor<T, Comm>(cm, FM, nullptr);
   qarrow_solve(cm, as_, FM, fs);
 
+#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 2      /* timing experiments only: + factor M and smooth solve */
+  s.wla += as_.la + as_.r[0];
+  return;
+#endif
+  JBQ_TICK(4);
   const int ncon = cm.isum(cs.n);
 
   // ---------------- constraint solve (primal Newton).  Control flow is kept WARP-uniform (Comm::warp_any): every quad
@@ -756,8 +780,12 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   QVec<T> a = as_;
   int iters = 0;
   const T mu = g[G_FRIC];
+#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 5      /* timing experiments only: contacts ignored by the solver */
+  const bool has_con = false;
+#else
   const bool has_con = ncon > 0;
-  if (cm.warp_any(has_con)) {
+#endif
+  if (cm.loop_any(has_con)) {              // uniform over the same scope as the Newton loop below
     QVec<T> aw;
     {
       T lw[3] = {s.wr[0], s.wr[1], s.wr[2]}, lr[3];
@@ -792,17 +820,30 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     for (int i = 0; i < 6; i++) grad.r[i] -= f7[i];
     grad.la -= fla; grad.lb -= flb; grad.mo -= f7[6];
     const int maxit = JbEps<T>::newton_iters();
+  JBQ_TICK(5);
     bool done = !has_con;
-    while (cm.warp_any(!done)) {
+#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 3      /* timing experiments only: warm-start selection, no Newton loop */
+    done = true; a.r[0] += grad.r[0] + grad.la;
+#endif
+    while (cm.loop_any(!done)) {           // CTA- or warp-uniform trip count (Comm decides)
+#ifdef JBQ_DEBUG_COUNT
+      if (lane == 0) g_jbq_newton_trips++;
+#endif
       QArrow<T> H = Mx;
       T part[28];
       jbq_hessian(H, part, cs, fr.Rw, mu);
+      cm.phase_sync(8);
       qarrow_factor<T, Comm>(cm, H, part);
+      cm.phase_sync(9);
       QVec<T> search;
       qarrow_solve(cm, search, H, grad);
 #pragma unroll
       for (int i = 0; i < 6; i++) search.r[i] = -search.r[i];
       search.la = -search.la; search.lb = -search.lb; search.mo = -search.mo;
+#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 4      /* timing experiments only: one Hessian + factor + solve */
+      a.r[0] += search.r[0] + search.la; done = true;
+      continue;
+#endif
       QVec<T> Mv;
       qarrow_mul(cm, Mv, Mx, search);
       for (int i = 0; i < cs.n; i++) {
@@ -810,6 +851,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         jbq_J_apply(u, cs.c[i], search);
         mulMV(cs.c[i].jv, fr.Rw, u);
       }
+      cm.phase_sync(10);
       res = Ma; qv_axpy(res, (T)-1, fs);
       // g1 = s.(Ma - fs), g2 = s.Mv, d0 = s.grad (= phi'(0)); at alpha = 1: contact part of phi' and phi''
       T red[6];
@@ -829,6 +871,9 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         const T tol = JbEps<T>::ls_tol() * jb_abs(d0);
         bool searching = !done && descent && !full && jb_abs(d) > tol;
         for (int it = 0; it < 30 && cm.warp_any(searching); it++) {
+#ifdef JBQ_DEBUG_COUNT
+          if (lane == 0) g_jbq_ls_iters++;
+#endif
           T an = alpha;
           if (searching) {
             if (d < (T)0) lo = alpha; else hi = alpha;
@@ -848,6 +893,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         }
       }
       if (done || !descent) alpha = 0;
+      cm.phase_sync(11);
       qv_axpy(a, alpha, search);
       qv_axpy(Ma, alpha, Mv);
       for (int i = 0; i < cs.n; i++) {
@@ -873,6 +919,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       }
     }
   }
+  JBQ_TICK(6);
   if (iter_accum) *iter_accum += iters;
   if (ncon_accum) *ncon_accum += ncon;
   if (overflow_accum) *overflow_accum += cm.isum(cs.overflow);
@@ -884,8 +931,6 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     s.wr[0] = lw[0]; s.wr[1] = lw[1]; s.wr[2] = lw[2]; s.wr[3] = a.r[3]; s.wr[4] = a.r[4]; s.wr[5] = a.r[5];
     s.wla = a.la; s.wlb = a.lb; s.wmo = a.mo;
   }
-  if (forward_only) return;
-
   // ---------------- semi-implicit Euler, implicit in joint damping: (M + hB) a' = f_s + f_c.  At the solver's fixed
   // point f_s + f_c = M a, so a' = a - (M + hB)^-1 (hB a) = a - M^-1 (hB a) + O((hB/M)^2 a): hB/M ~ 1e-3 on the leg
   // dofs, i.e. a relative error ~1e-6 of a 1e-3 correction.  Reuses the factor of M from the smooth solve.
@@ -930,6 +975,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   s.qm += h * s.vm;
   if (s.qm > (T)3.14159265358979323846) { s.qm -= (T)6.28318530717958647692; s.rev += 1; }
   else if (s.qm <= -(T)3.14159265358979323846) { s.qm += (T)6.28318530717958647692; s.rev -= 1; }
+  JBQ_TICK(7);
 #undef LX
 #undef LL
 }

@@ -7,7 +7,10 @@
 #include "../../include/jbsim.h"
 #include "jb_packed.h"
 
-#define JB_BLOCK 128                 /* threads per CTA = 32 quads = 32 envs */
+#ifndef JB_BLOCK
+#define JB_BLOCK 384                 /* threads per CTA; 4 threads (one quad) per env.  One 12-warp CTA per SM: measured
+                                        best trade-off between register budget (168) and instruction-stream sharing */
+#endif
 #define JB_ENVS_PER_BLOCK (JB_BLOCK / 4)
 
 // HBM layout: struct-of-arrays, env index fastest: qpos[16][N] (motor angle wrapped, revolutions in rev[N]),

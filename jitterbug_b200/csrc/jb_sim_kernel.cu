@@ -9,8 +9,14 @@
 #ifndef JB_SYNC_SUBSTEP
 #define JB_SYNC_SUBSTEP 1
 #endif
+#ifndef JB_BLOCK_NEWTON
+#define JB_BLOCK_NEWTON 0
+#endif
+#ifndef JB_PHASE_SYNC
+#define JB_PHASE_SYNC 0x7e      /* bit p: barrier at phase boundary p (1..6; 8..11 inside the Newton loop need JB_BLOCK_NEWTON) */
+#endif
 #ifndef JB_MIN_BLOCKS
-#define JB_MIN_BLOCKS 2
+#define JB_MIN_BLOCKS 1
 #endif
 
 // Quad sums as xor-butterflies over lanes {l, l^1, l^2, l^3}.  The kernel keeps control flow warp-uniform around every
@@ -32,6 +38,24 @@ struct QuadCommGPU {
     return v;
   }
   __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
+  __device__ __forceinline__ bool loop_any(bool p) {
+#if JB_BLOCK_NEWTON
+    return __syncthreads_or(p) != 0;     // CTA-uniform Newton trip count: allows barriers inside the loop
+#else
+    return __any_sync(0xffffffffu, p) != 0;
+#endif
+  }
+  // CTA barrier at the phase boundaries of the sub-step: the CTA's warps then execute the same few-KB code region at
+  // the same time and share its instruction-cache lines (the whole sub-step is several times the I-cache)
+  __device__ __forceinline__ void phase_sync(int p) {
+#if JB_PHASE_SYNC
+    if ((JB_PHASE_SYNC >> p) & 1) __syncthreads();
+#endif
+  }
+#ifdef JBQ_PHASE_TIMERS
+  long long t_last; long long acc[8];
+  __device__ __forceinline__ void tick(int p) { long long t = clock64(); if (p > 0) acc[p] += t - t_last; t_last = t; }
+#endif
 };
 
 __device__ __forceinline__ void load_state(const JbDev& d, int e, int lane, QState<float>& s) {
@@ -135,6 +159,10 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   const int e = min(e_raw, d.N - 1);
   const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_SIZE : jb_smem;
   QuadCommGPU cm;
+#ifdef JBQ_PHASE_TIMERS
+  for (int i = 0; i < 8; i++) cm.acc[i] = 0;
+  cm.t_last = clock64();
+#endif
   const int N = d.N;
   const int task = d.task[e];
   QState<float> s;
@@ -204,6 +232,9 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
     if (bad) atomicAdd(&d.counters[4], 1ull);
     if (e == 0) atomicAdd(&d.counters[0], (unsigned long long)d.n_sub * (unsigned long long)N);
   }
+#ifdef JBQ_PHASE_TIMERS
+  if ((tid & 31) == 0) for (int i = 1; i < 8; i++) atomicAdd(&d.counters[8 + i], (unsigned long long)cm.acc[i]);
+#endif
 }
 
 cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st) {
@@ -214,6 +245,9 @@ cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st
 }
 
 cudaError_t jb_configure_kernels(void) {
-  return cudaFuncSetAttribute(jb_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(JB_ENVS_PER_BLOCK * JBP_SIZE * sizeof(float)));
+  // per-env models stage JB_ENVS_PER_BLOCK packed models per CTA; opt in to as much dynamic shared memory as that needs
+  // (CTAs larger than 496 threads exceed the 227 KB limit in per-env mode and are rejected at launch)
+  size_t need = (size_t)JB_ENVS_PER_BLOCK * JBP_SIZE * sizeof(float);
+  if (need > 227 * 1024) need = 227 * 1024;
+  return cudaFuncSetAttribute(jb_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }

@@ -16,3 +16,8 @@ ev1.record(); torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1)/K
 c = env.counters()
 print(f"N={N} ms/step={ms:.3f} steps/s={N/ms*1e3:.3e} newton/substep={c['newton_iterations']/c['substeps']:.3f} ncon={c['contacts']/c['substeps']:.3f} ovf={c['contact_overflows']} div={c['diverged_resets']}")
+pc = env.phase_cycles()
+if sum(pc):
+    tot = sum(pc)
+    names = ["-", "leg kin+col", "root/rotor", "extra geoms", "factorM+solve", "warmstart sel", "newton loop", "euler"]
+    print("phases: " + ", ".join(f"{n}={100*c/tot:.1f}%" for n, c in zip(names, pc) if c))

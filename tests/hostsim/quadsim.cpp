@@ -2,6 +2,7 @@
 // The SPMD lane program runs unchanged in four ucontext fibers; Comm::sum* is a rendezvous that reproduces the GPU's
 // xor-butterfly summation order ((x_l + x_{l^1}) + (x_{l^2} + x_{l^3})), so the host result is what the kernel computes
 // (in fp64 for algorithmic parity, in fp32 for rounding behaviour).  Never loaded by the product package.
+#define JBQ_DEBUG_COUNT 1
 #include "../../jitterbug_b200/csrc/jb_quad.cuh"
 #include <string.h>
 #include <ucontext.h>
@@ -40,6 +41,8 @@ template <typename T> struct FiberComm {
   void sumN(T* v, int n) { exchange(v, n); }
   int isum(int v) { T x = (T)v; exchange(&x, 1); return (int)(x + (T)0.5); }
   bool warp_any(bool p) { return isum(p ? 1 : 0) > 0; }   // the emulated "warp" is one quad
+  bool loop_any(bool p) { return warp_any(p); }
+  void phase_sync(int) {}
 };
 
 template <typename T> struct Job {
@@ -136,6 +139,7 @@ int run(const T* P, T* qpos, T* qvel, T* warm, T ctrl, int nsub, int fwd, int* n
 }  // namespace
 
 extern "C" {
+void hq_debug_counts(long long* out) { out[0] = g_jbq_ls_iters; out[1] = g_jbq_newton_trips; }
 int hq_packed_size(void) { return JBP_SIZE; }
 void hq_pack_f64(const JbModelD* m, double* out) { jb_pack_model<double, JbModelD>(*m, out); }
 void hq_pack_f32(const JbModel* m, float* out) { jb_pack_model<float, JbModel>(*m, out); }
