@@ -58,7 +58,7 @@ def substeps(model_struct, qpos, qvel, warm, ctrl, nsub=1, double=True, want_dia
 # ------------------------------------------------------------------------------------------------ quad emulation
 _QSO = os.path.join(_HERE, "libquadsim.so")
 _QSRC = [os.path.join(_HERE, "quadsim.cpp")] + [os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", f)
-                                                 for f in ("jb_quad.cuh", "jb_math.cuh", "jb_packed.h", "jb_model.h")]
+                                                 for f in ("jb_quad.cuh", "jb_math.cuh", "jb_packed.h", "jb_model.h", "jb_task.cuh")]
 _qlib = None
 
 
@@ -100,3 +100,43 @@ def quad_substeps(packed, qpos, qvel, warm, ctrl, nsub=1, forward_only=False, wa
         raise RuntimeError("replicated quad state diverged between lanes")
     cons = sorted((int(g), float(d)) for g, d in zip(geom, dist) if g >= 0) if want_contacts else None
     return q, v, w, it, ncon.value, cons, ovf.value
+
+
+_DEFAULT_PACKED = None
+
+
+def default_packed_f32():
+    global _DEFAULT_PACKED
+    if _DEFAULT_PACKED is None:
+        from jitterbug_b200 import mjcf
+        _DEFAULT_PACKED = pack(jbmodel.fill_struct(jbmodel.flatten_model(mjcf.compile_xml())), double=False)
+    return _DEFAULT_PACKED
+
+
+def reset_states(seed, env_ids, episode, task, random_pose, packed=None):
+    """Host run of the device reset code: rows of (quat w,x,y,z, target x, y, qw, qz)."""
+    L = qlib()
+    P = default_packed_f32() if packed is None else packed
+    ids = np.ascontiguousarray(env_ids, dtype=np.uint32)
+    out = np.zeros((len(ids), 8), dtype=np.float32)
+    L.hq_reset_states(P.ctypes.data_as(C.c_void_p), C.c_ulonglong(seed), ids.ctypes.data_as(C.c_void_p), C.c_int(len(ids)),
+                      C.c_uint(episode), C.c_int(task), C.c_int(random_pose), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def obs_reward(qpos, qvel, task, target, packed=None):
+    L = qlib()
+    P = default_packed_f32() if packed is None else packed
+    q = np.ascontiguousarray(qpos, dtype=np.float32); v = np.ascontiguousarray(qvel, dtype=np.float32)
+    t = np.ascontiguousarray(target, dtype=np.float32)
+    obs = np.zeros(19, dtype=np.float32); rew = C.c_float()
+    n = L.hq_obs_reward(P.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_int(task),
+                        t.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p), C.byref(rew))
+    return obs[:n].copy(), rew.value
+
+
+def heuristic(task, obs):
+    L = qlib()
+    L.hq_heuristic.restype = C.c_float
+    o = np.zeros(19, dtype=np.float32); o[:len(obs)] = obs
+    return float(L.hq_heuristic(C.c_int(task), o.ctypes.data_as(C.c_void_p)))

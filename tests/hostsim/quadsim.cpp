@@ -4,6 +4,7 @@
 // (in fp64 for algorithmic parity, in fp32 for rounding behaviour).  Never loaded by the product package.
 #define JBQ_DEBUG_COUNT 1
 #include "../../jitterbug_b200/csrc/jb_quad.cuh"
+#include "../../jitterbug_b200/csrc/jb_task.cuh"
 #include <string.h>
 #include <ucontext.h>
 #include <vector>
@@ -139,6 +140,27 @@ int run(const T* P, T* qpos, T* qvel, T* warm, T ctrl, int nsub, int fwd, int* n
 }  // namespace
 
 extern "C" {
+// host instantiation of the device reset code: out[i] = quat(4), target x, y, qw, qz
+void hq_reset_states(const float* P, unsigned long long seed, const unsigned* env_ids, int n, unsigned episode, int task,
+                     int random_pose, float* out) {
+  for (int i = 0; i < n; i++) {
+    QState<float> s;
+    JbTarget<float> tg;
+    jb_reset_env<float>(P, s, tg, task, random_pose, seed, env_ids[i], episode);
+    for (int k = 0; k < 4; k++) out[8 * i + k] = s.quat[k];
+    out[8 * i + 4] = tg.x; out[8 * i + 5] = tg.y; out[8 * i + 6] = tg.qw; out[8 * i + 7] = tg.qz;
+  }
+}
+// host instantiation of the device obs/reward and heuristic code for one env
+int hq_obs_reward(const float* P, const float* qpos, const float* qvel, int task, const float* tgt, float* obs, float* rew) {
+  QState<float> s;
+  for (int i = 0; i < 3; i++) { s.pos[i] = qpos[i]; s.vlin[i] = qvel[i]; s.w[i] = qvel[3 + i]; }
+  for (int i = 0; i < 4; i++) s.quat[i] = qpos[3 + i];
+  s.qm = qpos[15]; s.vm = qvel[14];
+  JbTarget<float> tg = {tgt[0], tgt[1], tgt[2], tgt[3]};
+  return jb_obs_reward<float>(P, s, task, tg, obs, rew);
+}
+float hq_heuristic(int task, const float* obs) { return jb_heuristic<float>(task, obs); }
 void hq_debug_counts(long long* out) { out[0] = g_jbq_ls_iters; out[1] = g_jbq_newton_trips; }
 int hq_packed_size(void) { return JBP_SIZE; }
 void hq_pack_f64(const JbModelD* m, double* out) { jb_pack_model<double, JbModelD>(*m, out); }

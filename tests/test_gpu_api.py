@@ -1,0 +1,165 @@
+"""GPU tests of the drop-in Python surface: suite.load / TimeStep semantics / specs / gym wrapper / heuristics solve the
+tasks / per-env augmented models / shard invariance."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_suite_load_timestep_semantics():
+    _need_gpu()
+    from jitterbug_b200 import suite
+    env = suite.load(domain_name="jitterbug", task_name="move_in_direction", task_kwargs=dict(random=1, time_limit=0.05))
+    assert env._step_limit == 5.0 and env.control_timestep() == pytest.approx(0.01)
+    spec = env.action_spec()
+    assert spec.shape == (1,) and spec.minimum[0] == -1 and spec.maximum[0] == 1 and spec.dtype == np.float64
+    ospec = env.observation_spec()
+    assert list(ospec) == ["position", "velocity", "motor_position", "motor_velocity", "angle_to_target",
+                           "speed_in_target_frame"]
+    assert [v.shape for v in ospec.values()] == [(7,), (6,), (1,), (1,), (1,), (3,)]
+    ts = env.step([0.3])                       # step before reset is a reset
+    assert ts.first() and ts.reward is None and ts.discount is None
+    for k in range(4):
+        ts = env.step(np.array([0.5]))
+        assert ts.mid() and ts.discount == 1.0 and 0.0 <= ts.reward <= 1.0
+        assert ts.observation["position"].dtype == np.float64 and ts.observation["position"].shape == (7,)
+    ts = env.step(0.5)
+    assert ts.last() and ts.discount == 1.0
+    ts = env.step(0.5)
+    assert ts.first()
+    # physics helpers
+    p = env.physics
+    assert p.jitterbug_position().shape == (7,) and p.target_position().shape == (7,)
+    assert p.angle_jitterbug_to_target().shape == (1,) and -np.pi < p.angle_jitterbug_to_target()[0] <= np.pi
+    assert p.target_position_in_jitterbug_frame().shape == (3,)
+    env.close()
+
+
+def test_flat_observation_and_gym_wrapper():
+    _need_gpu()
+    from jitterbug_b200 import suite, JitterbugGymEnv
+    env = JitterbugGymEnv(suite.load("jitterbug", "move_to_pose", task_kwargs=dict(random=0),
+                                     environment_kwargs=dict(flat_observation=True)))
+    assert env.num_envs == 1
+    obs = env.reset()
+    assert list(obs) == ["observations"] and obs["observations"].shape == (19,)
+    for t in range(5):
+        obs, reward, done, info = env.step(0.8)
+        assert not done and info == {} and 0 <= reward <= 1
+    env.close()
+
+
+@pytest.mark.parametrize("task", ["move_from_origin", "face_direction", "move_to_position"])
+def test_heuristic_policies_make_progress(task):
+    """Behavioural pin from the paper (root_post.tex:392: the heuristic policies can solve each task): over 400 control
+    steps the batched device heuristics earn far more reward than a zero policy."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv
+    N = 256
+    env = BatchedJitterbugEnv(task, num_envs=N, seed=11)
+    obs = env.reset()
+    ret = torch.zeros(N, device=env.device)
+    for _ in range(400):
+        obs, rew, _ = env.step(env.heuristic_actions(obs))
+        ret += rew
+    env0 = BatchedJitterbugEnv(task, num_envs=N, seed=11)
+    env0.reset()
+    ret0 = torch.zeros(N, device=env.device)
+    for _ in range(400):
+        _, rew, _ = env0.step(torch.zeros(N, device=env.device))
+        ret0 += rew
+    assert ret.mean().item() > ret0.mean().item() + 20, (ret.mean().item(), ret0.mean().item())
+    c = env.counters()
+    assert c["diverged_resets"] == 0
+
+
+def test_single_env_heuristic_policy_through_timestep_api():
+    _need_gpu()
+    from jitterbug_b200 import suite, heuristic_policies
+    env = suite.load("jitterbug", "move_from_origin", task_kwargs=dict(random=2))
+    ts = env.reset()
+    total = 0.0
+    for _ in range(150):
+        ts = env.step(heuristic_policies.move_from_origin(ts))
+        total += ts.reward
+    assert np.isfinite(total) and total >= 0
+    env.close()
+
+
+def test_per_env_augmented_models_match_oracle():
+    """Config 4: every env carries its own perturbed model; one control step vs the oracle built on the same model."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv, augmented_jitterbug
+    from oracle import oracle as O
+    models = augmented_jitterbug.make_models(6, seed=3)
+    N = 48
+    per_env = [models[i % 6] for i in range(N)]
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=4, models=per_env)
+    env.reset()
+    g = torch.Generator(device=env.device).manual_seed(1)
+    for _ in range(40):
+        env.step(torch.rand(N, device=env.device, generator=g) * 2 - 1)
+    qpos, qvel, warm = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+    a = torch.rand(N, device=env.device, generator=g) * 2 - 1
+    env.step(a)
+    q1, v1, _ = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+    a = a.cpu().numpy()
+    errs = []
+    sims = [O.OracleSim(m) for m in models]
+    for e in range(N):
+        sim = sims[e % 6]
+        sim.set_state(qpos[e], qvel[e], warm[e])
+        sim.step1()
+        sim.control_step(a[e], 50)
+        errs.append(np.abs(q1[e] - sim.qpos).max())
+    errs = np.array(errs)
+    assert np.median(errs) < 2e-5, np.median(errs)
+    assert np.quantile(errs, 0.9) < 2e-3
+    # and the models really differ: same state, shared-model env gives a different answer
+    env_shared = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=4)
+    env_shared.reset()
+    env_shared.set_state(qpos, qvel, warm, step_count=np.ones(N))
+    env_shared.step(torch.as_tensor(a, dtype=torch.float32, device=env.device))
+    q2 = env_shared.get_state()[0].cpu().numpy()
+    assert np.abs(q2 - q1).max() > 1e-5
+
+
+def test_results_do_not_depend_on_sharding():
+    """Two shards with env_id_offset reproduce the single big batch bit-for-bit (Philox keyed by global env id)."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv
+    N = 192
+    acts = torch.rand(10, N, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(5)) * 2 - 1
+    big = BatchedJitterbugEnv("move_to_pose", num_envs=N, seed=9)
+    a = BatchedJitterbugEnv("move_to_pose", num_envs=N // 2, seed=9, env_id_offset=0)
+    b = BatchedJitterbugEnv("move_to_pose", num_envs=N // 2, seed=9, env_id_offset=N // 2)
+    o_big = big.reset().clone()
+    o_ab = torch.cat([a.reset(), b.reset()])
+    assert torch.equal(o_big, o_ab)
+    for k in range(10):
+        ob, rb, _ = big.step(acts[k])
+        oa, ra, _ = a.step(acts[k, :N // 2])
+        oa = oa.clone(); ra = ra.clone()
+        o2, r2, _ = b.step(acts[k, N // 2:])
+        assert torch.equal(ob, torch.cat([oa, o2])) and torch.equal(rb, torch.cat([ra, r2]))
+
+
+def test_mixed_task_batch():
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv, TASKS
+    N = 320
+    tasks = [TASKS[i % 5] for i in range(N)]
+    env = BatchedJitterbugEnv(tasks, num_envs=N, seed=2)
+    obs = env.reset()
+    assert obs.shape == (N, 19)
+    for _ in range(20):
+        obs, rew, st = env.step(env.heuristic_actions(obs))
+    assert torch.isfinite(obs).all() and ((rew >= 0) & (rew <= 1)).all()
+    # padded columns stay zero for the narrower tasks
+    assert (obs[0::5, 15:] == 0).all() and (obs[1::5, 16:] == 0).all() and (obs[3::5, 18:] == 0).all()

@@ -1,0 +1,70 @@
+"""The quad (4 lanes per env) algorithm the CUDA kernel runs, emulated on the host with fibers (tests/hostsim/quadsim.cpp),
+against the oracle along fresh rollouts (the golden test covers fixed vectors)."""
+import numpy as np
+import pytest
+
+import hostsim
+from helpers import random_state
+from jitterbug_b200 import model as jbm
+from oracle import oracle as O
+
+
+@pytest.fixture(scope="module")
+def packed(compiled_model):
+    flat = jbm.flatten_model(compiled_model)
+    return hostsim.pack(jbm.fill_struct(flat, double=True), True), hostsim.pack(jbm.fill_struct(flat, double=False), False)
+
+
+def test_airborne_states_fp64(compiled_model, packed):
+    Pd, _ = packed
+    sim = O.OracleSim(compiled_model)
+    rng = np.random.default_rng(0)
+    for _ in range(6):
+        q, v = random_state(compiled_model, rng)
+        sim.set_state(q, v, ctrl=-0.7)
+        sim.step1()
+        sim.step2()
+        q1, v1, w1, it, ncon, _, _ = hostsim.quad_substeps(Pd, q, v, np.zeros(15), -0.7)
+        assert ncon == 0 and it == 0
+        np.testing.assert_allclose(q1, sim.qpos, atol=1e-13)
+        np.testing.assert_allclose(v1, sim.qvel, atol=1e-9)
+
+
+def test_rollout_substeps_fp64(compiled_model, packed):
+    Pd, _ = packed
+    sim = O.OracleSim(compiled_model)
+    rng = np.random.default_rng(21)
+    sim.qpos[3:7] = [np.cos(1.0), 0.02 * np.sin(1.0), 0.01 * np.sin(1.0), np.sin(1.0)]
+    sim.forward()
+    n = 0
+    for cs in range(30):
+        ctrl = rng.uniform(-1, 1)
+        sim.d.ctrl[0] = ctrl
+        for k in range(50):
+            q, v, w = sim.qpos.copy(), sim.qvel.copy(), sim.warmstart.copy()
+            g2, dist, excl, _ = sim.contacts()
+            sim.physics_step()
+            if any(abs(d) < 1e-9 for d in dist):
+                continue
+            q1, v1, w1, it, ncon, cons, ovf = hostsim.quad_substeps(Pd, q, v, w, ctrl, 1, False, True)
+            assert [c for c, _ in cons] == sorted(int(g) for g, x in zip(g2, excl) if not x)
+            np.testing.assert_allclose(q1, sim.qpos, atol=1e-12)
+            np.testing.assert_allclose(v1, sim.qvel, atol=5e-9)
+            n += 1
+    assert n > 1400
+
+
+def test_forward_only_is_a_zero_length_step(compiled_model, packed):
+    Pd, _ = packed
+    sim = O.OracleSim(compiled_model)
+    sim.qpos[3:7] = [np.cos(0.2), 0, 0.02 * np.sin(0.2), np.sin(0.2)]
+    sim.forward()
+    for _ in range(20):
+        sim.control_step(0.4)
+    q, v, w = sim.qpos.copy(), sim.qvel.copy(), sim.warmstart.copy()
+    sim.set_state(q, v, np.zeros(15), ctrl=0.0)
+    sim.forward()
+    q1, v1, w1, *_ = hostsim.quad_substeps(Pd, q, v, np.zeros(15), 0.0, 1, True)
+    np.testing.assert_allclose(q1[:3], q[:3], atol=0)
+    np.testing.assert_allclose(v1, v, atol=0)
+    np.testing.assert_allclose(w1, sim.warmstart, rtol=1e-6, atol=1e-5)
