@@ -55,10 +55,12 @@ def test_flat_observation_and_gym_wrapper():
     env.close()
 
 
-@pytest.mark.parametrize("task", ["move_from_origin", "face_direction", "move_to_position"])
+@pytest.mark.parametrize("task", ["move_from_origin", "face_direction"])
 def test_heuristic_policies_make_progress(task):
     """Behavioural pin from the paper (root_post.tex:392: the heuristic policies can solve each task): over 400 control
-    steps the batched device heuristics earn far more reward than a zero policy."""
+    steps the batched device heuristics earn far more reward than a zero policy.  (The position tasks are not asserted:
+    at HEAD the heuristics compare radian thresholds with *normalised* angles, SURVEY.md App. C7, which widens the
+    kick window from +-45 deg to +-141 deg and makes the bug walk backwards -- ported literally, see the next test.)"""
     _need_gpu()
     from jitterbug_b200 import BatchedJitterbugEnv
     N = 256
@@ -77,6 +79,30 @@ def test_heuristic_policies_make_progress(task):
     assert ret.mean().item() > ret0.mean().item() + 20, (ret.mean().item(), ret0.mean().item())
     c = env.counters()
     assert c["diverged_resets"] == 0
+
+
+def test_kick_controller_in_radians_walks_forward():
+    """Physics plausibility pin: the kick controller as designed (motor angle in radians, +-45 deg window around
+    "forwards" = body -Y, jitterbug.py:204-206, heuristic_policies.py:28-56) drives the bug along its -Y axis."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv
+    N = 256
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=3)
+    obs = env.reset()
+    q0 = env.get_state()[0].clone()
+    for _ in range(500):
+        ang = obs[:, 13] * np.pi          # de-normalised motor angle
+        vel = obs[:, 14]
+        act = torch.where(ang < -np.pi / 4, 0.3, torch.where(ang > np.pi / 4, -0.3, torch.where(vel > 0, 0.3, -0.3)))
+        obs, _, _ = env.step(act.float())
+    q1 = env.get_state()[0]
+    d = q1[:, 0:2] - q0[:, 0:2]
+    w, x, y, z = q1[:, 3], q1[:, 4], q1[:, 5], q1[:, 6]
+    # world displacement projected on the body's y axis (second column of R)
+    ry = torch.stack([2 * (x * y - w * z), w * w - x * x + y * y - z * z], dim=1)
+    along_y = (d * ry).sum(dim=1)
+    assert along_y.median().item() < -0.03, along_y.median().item()
+    assert (along_y < 0).float().mean().item() > 0.85
 
 
 def test_single_env_heuristic_policy_through_timestep_api():
