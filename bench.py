@@ -140,7 +140,7 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_env, n_steps = 4 * cores, 10          # one "step" of this arm = a bounded sample: 4*cores envs x 10 control steps
+    n_env, n_steps = 16 * cores, 100        # one "step" of this arm = a bounded sample: 16*cores envs x 100 control steps
     for _ in range(max(args.warmup, 0)):
         cpu_rollout_rate(n_env, 2, cores)
     rates, times = [], []
@@ -191,6 +191,10 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # untimed burn-in to the stationary regime (motor spun up, contacts active: BASELINE.md section 4 asks for
+    # ~200 control steps before sampling), then the W warm-up steps of the contract
+    for i in range(args.burn_in):
+        env.step(acts[i % n_act])
     for i in range(args.warmup):
         env.step(acts[i % n_act])
     barrier()
@@ -251,7 +255,7 @@ def run_cuda(args):
         cores = os.cpu_count() or 1
         cpu = None
         if world >= 1 and not args.no_cpu_baseline:
-            n_env, n_steps = 4 * cores, 40
+            n_env, n_steps = 16 * cores, 1000          # one full 1000-step episode per env, ~5-20 s of CPU work
             rate, dt, _ = cpu_rollout_rate(n_env, n_steps, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n_env} envs x {n_steps} control steps ({dt:.1f} s), fp64 C oracle port, {cores} pthreads"}
@@ -265,6 +269,7 @@ def run_cuda(args):
                        f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per step vs 126 MB L2)"
                        if BYTES_PER_ENV_STEP * E > 126e6 else "inputs smaller than L2 (compute-bound kernel)",
                        "parallelism": f"env-sharded x{world}, no collective in the step path",
+                       "burn_in_steps": args.burn_in,
                        "newton_iters_per_substep": newton, "contacts_per_substep": ncon,
                        "mean_reward": mean_reward},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E,
@@ -295,6 +300,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
