@@ -759,57 +759,33 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   return;
 #endif
   JBQ_TICK(3);
-  // ---------------- smooth dynamics: f_s = passive + actuator - bias ; a_s = M^-1 f_s
+  // ---------------- smooth force: f_s = passive + actuator - bias.  The unconstrained acceleration a_s = M^-1 f_s is
+  // never formed: the primal Newton solver only needs f_s (gradient M a - f_s - J'f), it starts from the warm start,
+  // and the contact-free case goes straight to the implicit-damping Euler solve below.
   QVec<T> fs = fpass;
   qv_axpy(fs, (T)-1, bias);
-  QVec<T> as_;
-  QArrow<T> FM = Mx;
-  qarrow_factor<T, Comm>(cm, FM, nullptr);
-  qarrow_solve(cm, as_, FM, fs);
-
-#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 2      /* timing experiments only: + factor M and smooth solve */
-  s.wla += as_.la + as_.r[0];
-  return;
-#endif
   JBQ_TICK(4);
   const int ncon = cm.isum(cs.n);
 
   // ---------------- constraint solve (primal Newton).  Control flow is kept WARP-uniform (Comm::warp_any): every quad
   // of the warp runs the same number of Newton / line-search iterations, quads that are finished take zero-length
   // steps.  That is what SIMT divergence would cost anyway, and it lets every quad shuffle run with the full mask.
-  QVec<T> a = as_;
+  QVec<T> a, fcon;
+  qv_zero(a); qv_zero(fcon);
   int iters = 0;
   const T mu = g[G_FRIC];
-#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 5      /* timing experiments only: contacts ignored by the solver */
-  const bool has_con = false;
-#else
   const bool has_con = ncon > 0;
-#endif
   if (cm.loop_any(has_con)) {              // uniform over the same scope as the Newton loop below
-    QVec<T> aw;
     {
+      // start from qacc_warmstart (MuJoCo starts from the better of warm start and a_s; the minimiser is the same)
       T lw[3] = {s.wr[0], s.wr[1], s.wr[2]}, lr[3];
       mulMTV(lr, fr.Rw, lw);
-      aw.r[0] = lr[0]; aw.r[1] = lr[1]; aw.r[2] = lr[2]; aw.r[3] = s.wr[3]; aw.r[4] = s.wr[4]; aw.r[5] = s.wr[5];
-      aw.la = s.wla; aw.lb = s.wlb; aw.mo = s.wmo;
+      a.r[0] = lr[0]; a.r[1] = lr[1]; a.r[2] = lr[2]; a.r[3] = s.wr[3]; a.r[4] = s.wr[4]; a.r[5] = s.wr[5];
+      a.la = s.wla; a.lb = s.wlb; a.mo = s.wmo;
     }
-    QVec<T> Ma;
-    qarrow_mul(cm, Ma, Mx, aw);
-    // total cost at the warm start and at the unconstrained acceleration (mj_fwdConstraint warmstart selection)
-    QVec<T> res = Ma; qv_axpy(res, (T)-1, fs);
-    QVec<T> da = aw; qv_axpy(da, (T)-1, as_);
-    jbq_eval_ww(cs, fr.Rw, aw);
-    T cw = jbq_cost(cs, mu) + (T)0.5 * qv_dot_leg(res, da);
-    jbq_eval_ww(cs, fr.Rw, as_);
-    T csm = jbq_cost(cs, mu);
-    cm.sum2(cw, csm);
-    cw += (T)0.5 * qv_dot_rep(res, da);
-    if (cw > csm || !has_con) {
-      a = as_; Ma = fs;                 // M a_s = f_s ; ww already evaluated at a_s
-    } else {
-      a = aw;
-      jbq_eval_ww(cs, fr.Rw, a);
-    }
+    QVec<T> Ma, res;
+    qarrow_mul(cm, Ma, Mx, a);
+    jbq_eval_ww(cs, fr.Rw, a);
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
     T f7[8], fla, flb;
     uint32_t mask = jbq_forces(cs, fr.Rw, mu, f7, &fla, &flb);
@@ -820,7 +796,6 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     for (int i = 0; i < 6; i++) grad.r[i] -= f7[i];
     grad.la -= fla; grad.lb -= flb; grad.mo -= f7[6];
     const int maxit = JbEps<T>::newton_iters();
-  JBQ_TICK(5);
     bool done = !has_con;
 #if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 3      /* timing experiments only: warm-start selection, no Newton loop */
     done = true; a.r[0] += grad.r[0] + grad.la;
@@ -918,37 +893,35 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         if (!descent || (full && f8[7] == (T)0) || gn < JbEps<T>::newton_tol() || iters >= maxit) done = true;
       }
     }
+    // constraint force at the solution: f_c = f_s-residual form, f_c = M a - f_s - grad
+    fcon = Ma;
+    qv_axpy(fcon, (T)-1, fs); qv_axpy(fcon, (T)-1, grad);
   }
   JBQ_TICK(6);
   if (iter_accum) *iter_accum += iters;
   if (ncon_accum) *ncon_accum += ncon;
   if (overflow_accum) *overflow_accum += cm.isum(cs.overflow);
 
-  // ---------------- save warm start (MuJoCo coordinates)
+  // ---------------- semi-implicit Euler, implicit in joint damping: (M + hB) a' = f_s + f_c  (mj_Euler)
+  QVec<T> aeu;
+  {
+    QVec<T> rhs = fs;
+    qv_axpy(rhs, (T)1, fcon);
+    QArrow<T> F = Mx;
+    F.aa += h * LL(L_D1); F.bb += h * LL(L_D2); F.mm += h * g[G_DAMPM];
+    qarrow_factor<T, Comm>(cm, F, nullptr);
+    qarrow_solve(cm, aeu, F, rhs);
+  }
+  // ---------------- save warm start (MuJoCo coordinates).  Without contacts qacc = M^-1 f_s in MuJoCo; the Euler
+  // acceleration (which differs by the O(hB/M) damping term) is kept instead: it is only the next solve's initial guess.
+  if (!has_con) a = aeu;
   {
     T lw[3];
     mulMV(lw, fr.Rw, a.r);
     s.wr[0] = lw[0]; s.wr[1] = lw[1]; s.wr[2] = lw[2]; s.wr[3] = a.r[3]; s.wr[4] = a.r[4]; s.wr[5] = a.r[5];
     s.wla = a.la; s.wlb = a.lb; s.wmo = a.mo;
   }
-  // ---------------- semi-implicit Euler, implicit in joint damping: (M + hB) a' = f_s + f_c.  At the solver's fixed
-  // point f_s + f_c = M a, so a' = a - (M + hB)^-1 (hB a) = a - M^-1 (hB a) + O((hB/M)^2 a): hB/M ~ 1e-3 on the leg
-  // dofs, i.e. a relative error ~1e-6 of a 1e-3 correction.  Reuses the factor of M from the smooth solve.
-  {
-    // Neumann series a' = sum_k (-M^-1 hB)^k a: one term is below fp32 resolution, fp64 (test build) takes four
-    const int nterms = sizeof(T) == 8 ? 4 : 1;
-    QVec<T> term = a;
-    T sign = (T)-1;
-    for (int k = 0; k < nterms; k++) {
-      QVec<T> hb, dl;
-      qv_zero(hb);
-      hb.la = h * LL(L_D1) * term.la; hb.lb = h * LL(L_D2) * term.lb; hb.mo = h * g[G_DAMPM] * term.mo;
-      qarrow_solve(cm, dl, FM, hb);
-      qv_axpy(a, sign, dl);
-      term = dl;
-      sign = -sign;
-    }
-  }
+  a = aeu;
   {
     T lw[3];
     mulMV(lw, fr.Rw, a.r);
