@@ -24,6 +24,18 @@ JB_HD void jb_sincos(float x, float* s, float* c) {
 #endif
 }
 JB_HD void jb_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+// sin / cos for small arguments (leg hinge angles, the per-step quaternion increment): Taylor series to x^11 / x^10 are
+// exact to fp32 rounding for |x| <= 0.5; larger arguments fall back to the library call.
+JB_HD void jb_sincos_small(float x, float* s, float* c) {
+  if (fabsf(x) <= 0.5f) {
+    const float x2 = x * x;
+    *s = x * (1.f + x2 * (-1.f / 6 + x2 * (1.f / 120 + x2 * (-1.f / 5040 + x2 * (1.f / 362880 + x2 * (-1.f / 39916800))))));
+    *c = 1.f + x2 * (-0.5f + x2 * (1.f / 24 + x2 * (-1.f / 720 + x2 * (1.f / 40320 + x2 * (-1.f / 3628800)))));
+  } else {
+    jb_sincos(x, s, c);
+  }
+}
+JB_HD void jb_sincos_small(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 template <typename T> JB_HD T jb_max(T a, T b) { return a > b ? a : b; }
 template <typename T> JB_HD T jb_min(T a, T b) { return a < b ? a : b; }
 template <typename T> struct JbEps;

@@ -50,9 +50,12 @@ template <typename T> struct QArrow {   // R, cm, mm replicated; aa..cb this lan
 };
 enum { QK_LEG = 0, QK_ROOT = 1, QK_ROTOR = 2 };
 template <typename T> struct QCon {
-  T x[3], D, ar0, uref[3];              // point (root comps), 1/Rpy, -K*imp*dist, -B*v_point (WORLD comps)
+  // world-frame rows of the 3 x 8 contact Jacobian over (root lin 3, root ang 3, jA, jB): u_world = J (a_root, qA, qB)
+  // with (qA, qB) = (la, lb) of this lane's leg, or (motor, -) for a rotor contact.  Row k = [r_k, x cross r_k, r_k.ja,
+  // r_k.jb], r_k = world axis k in root coordinates.  Built once when the contact is created.
+  T Jx[8], Jy[8], Jz[8];
+  T D, ar0, uref[3];                    // 1/Rpy, -K*imp*dist, -B*v_point (WORLD comps)
   T ww[3], jv[3];                       // solver scratch (WORLD comps): J a - uref ; J search
-  T ja[3], jb[3];                       // joint Jacobian columns (root comps): leg hinge 1 / 2, or motor in ja
   int kind;
 };
 template <typename T> struct QConSet { QCon<T> c[JBQ_CAP]; int n, overflow; };
@@ -232,15 +235,23 @@ JB_COLD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBo
   if (i >= JBQ_CAP) { cs.overflow = 1; return; }
   cs.n = i + 1;
   QCon<T>& c = cs.c[i];
-  c.x[0] = x[0]; c.x[1] = x[1]; c.x[2] = x[2];
   c.kind = b.kind;
-  T v[3], t[3], r[3];
-  cross3(t, fr.w, x);
-  v[0] = fr.vr[0] + t[0]; v[1] = fr.vr[1] + t[1]; v[2] = fr.vr[2] + t[2];
-  c.ja[0] = c.ja[1] = c.ja[2] = (T)0; c.jb[0] = c.jb[1] = c.jb[2] = (T)0;
+  T ja[3] = {0, 0, 0}, jb[3] = {0, 0, 0}, r[3];
   if (b.kind != QK_ROOT) {
-    sub3(r, x, b.p1); cross3(c.ja, b.a1, r); addscl3(v, c.ja, b.qd1);
-    if (b.lower) { sub3(r, x, b.p2); cross3(c.jb, b.a2, r); addscl3(v, c.jb, b.qd2); }
+    sub3(r, x, b.p1); cross3(ja, b.a1, r);
+    if (b.lower) { sub3(r, x, b.p2); cross3(jb, b.a2, r); }
+  }
+  T* const rows[3] = {c.Jx, c.Jy, c.Jz};
+  // point velocity in WORLD comps from the same rows: v_w[k] = J_k . (vr, w, qdA, qdB)
+  T vw[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    T* J = rows[k];
+    const T* rk = fr.Rw + 3 * k;
+    J[0] = rk[0]; J[1] = rk[1]; J[2] = rk[2];
+    cross3(J + 3, x, rk);
+    J[6] = dot3(rk, ja); J[7] = dot3(rk, jb);
+    vw[k] = dot3(J, fr.vr) + dot3(J + 3, fr.w) + J[6] * b.qd1 + J[7] * b.qd2;
   }
   T imp = jbq_impedance<T>(g + G_SOLIMP, dist);
   T mu = g[G_FRIC];
@@ -248,8 +259,6 @@ JB_COLD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBo
   T Rpy = (T)2 * mu * mu / g[G_IMPRATIO] * ((T)1 - imp) / imp * b.invw * ((T)1 + mu * mu);
   c.D = (T)1 / jb_max(Rpy, (T)1e-15);
   c.ar0 = -g[G_SOLK] * imp * dist;
-  T vw[3];
-  mulMV(vw, fr.Rw, v);
   c.uref[0] = -g[G_SOLB] * vw[0]; c.uref[1] = -g[G_SOLB] * vw[1]; c.uref[2] = -g[G_SOLB] * vw[2];
   if (rep) { rep->geom[(lane * JBQ_CAP + i) * rep->stride] = geom; rep->dist[(lane * JBQ_CAP + i) * rep->stride] = dist; }
 }
@@ -359,99 +368,87 @@ template <typename T> JB_HD void jbq_rows(T* jar, const T* ww, T mu, T ar0) {
   jar[3] = ww[2] + mu * ww[0] - ar0;
 }
 
-// u = J_c a in ROOT comps
-template <typename T> JB_HD void jbq_J_apply(T* u, const QCon<T>& c, const QVec<T>& a) {
-  T t[3];
-  cross3(t, a.r + 3, c.x);
-  T qa = c.kind == QK_ROTOR ? a.mo : a.la;
-  u[0] = a.r[0] + t[0] + c.ja[0] * qa + c.jb[0] * a.lb;
-  u[1] = a.r[1] + t[1] + c.ja[1] * qa + c.jb[1] * a.lb;
-  u[2] = a.r[2] + t[2] + c.ja[2] * qa + c.jb[2] * a.lb;
+// out = J_c a in WORLD comps
+template <typename T> JB_HD void jbq_J_apply(T* out, const QCon<T>& c, const QVec<T>& a) {
+  const T qa = c.kind == QK_ROTOR ? a.mo : a.la;
+  const T* const rows[3] = {c.Jx, c.Jy, c.Jz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const T* J = rows[k];
+    T s = J[6] * qa + J[7] * a.lb;
+#pragma unroll
+    for (int i = 0; i < 6; i++) s += J[i] * a.r[i];
+    out[k] = s;
+  }
 }
 
-template <typename T> JB_HD void jbq_eval_ww(QConSet<T>& cs, const T* Rw, const QVec<T>& a) {
+// ww = J_c a - uref (dst = 0) or jv = J_c a (dst = 1) for every contact of this lane
+template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a, int dst) {
   for (int i = 0; i < cs.n; i++) {
     QCon<T>& c = cs.c[i];
-    T u[3], uw[3];
+    T u[3];
     jbq_J_apply(u, c, a);
-    mulMV(uw, Rw, u);
-    c.ww[0] = uw[0] - c.uref[0]; c.ww[1] = uw[1] - c.uref[1]; c.ww[2] = uw[2] - c.uref[2];
+    if (dst == 0) { c.ww[0] = u[0] - c.uref[0]; c.ww[1] = u[1] - c.uref[1]; c.ww[2] = u[2] - c.uref[2]; }
+    else { c.jv[0] = u[0]; c.jv[1] = u[1]; c.jv[2] = u[2]; }
   }
 }
 
-template <typename T> JB_HD T jbq_cost(const QConSet<T>& cs, T mu) {
-  T cost = 0;
-  for (int i = 0; i < cs.n; i++) {
-    T jar[4];
-    jbq_rows(jar, cs.c[i].ww, mu, cs.c[i].ar0);
-#pragma unroll
-    for (int r = 0; r < 4; r++) if (jar[r] < (T)0) cost += (T)0.5 * cs.c[i].D * jar[r] * jar[r];
-  }
-  return cost;
-}
-
-// This lane's constraint forces at the current ww: writes the partial generalized force (root 6 + motor partial in
-// out[6], leg in *fla, *flb) and returns the lane's active-row mask (4 bits per contact).
+// One pass over this lane's contacts at the current ww: constraint forces (partial generalized force: root 6 + motor
+// partial in out7[6], leg in *fla / *flb), the Hessian terms J' W J (leg block into H, replicated block into part[28]),
+// and the active-row mask (4 bits per contact).  W = sum over active rows of D e e' has 5 distinct entries for the
+// pyramid {z +- mu y, z -+ mu x}.
 template <typename T>
-JB_HD uint32_t jbq_forces(const QConSet<T>& cs, const T* Rw, T mu, T* out7, T* fla, T* flb) {
+JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, QArrow<T>& H, T* part) {
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 7; i++) out7[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 28; i++) part[i] = 0;
   *fla = 0; *flb = 0;
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
     T jar[4];
     jbq_rows(jar, c.ww, mu, c.ar0);
-    T f0 = jar[0] < (T)0 ? -c.D * jar[0] : (T)0, f1 = jar[1] < (T)0 ? -c.D * jar[1] : (T)0;
-    T f2 = jar[2] < (T)0 ? -c.D * jar[2] : (T)0, f3 = jar[3] < (T)0 ? -c.D * jar[3] : (T)0;
+    const T a0 = jar[0] < (T)0 ? (T)1 : (T)0, a1 = jar[1] < (T)0 ? (T)1 : (T)0;
+    const T a2 = jar[2] < (T)0 ? (T)1 : (T)0, a3 = jar[3] < (T)0 ? (T)1 : (T)0;
     mask |= ((jar[0] < (T)0 ? 1u : 0u) | (jar[1] < (T)0 ? 2u : 0u) | (jar[2] < (T)0 ? 4u : 0u) | (jar[3] < (T)0 ? 8u : 0u)) << (4 * i);
-    T fw[3] = {mu * (f3 - f2), mu * (f0 - f1), f0 + f1 + f2 + f3}, fr[3], t[3];
-    mulMTV(fr, Rw, fw);
-    out7[0] += fr[0]; out7[1] += fr[1]; out7[2] += fr[2];
-    cross3(t, c.x, fr);
-    out7[3] += t[0]; out7[4] += t[1]; out7[5] += t[2];
-    T ga = dot3(c.ja, fr), gb = dot3(c.jb, fr);
-    if (c.kind == QK_ROTOR) out7[6] += ga; else *fla += ga;
-    *flb += gb;
-  }
-  return mask;
-}
-
-// Hessian contact terms of this lane: leg block added to H in place, replicated block returned in part[28]
-template <typename T>
-JB_HD void jbq_hessian(QArrow<T>& H, T* part, const QConSet<T>& cs, const T* Rw, T mu) {
+    const T f0 = -c.D * jar[0] * a0, f1 = -c.D * jar[1] * a1, f2 = -c.D * jar[2] * a2, f3 = -c.D * jar[3] * a3;
+    const T fw0 = mu * (f3 - f2), fw1 = mu * (f0 - f1), fw2 = f0 + f1 + f2 + f3;
+    const T dm = c.D * mu;
+    const T Wzz = c.D * (a0 + a1 + a2 + a3), Wyz = dm * (a0 - a1), Wxz = dm * (a3 - a2);
+    const T Wyy = dm * mu * (a0 + a1), Wxx = dm * mu * (a2 + a3);
+    T Gx[8], Gy[8], Gz[8];
 #pragma unroll
-  for (int i = 0; i < 28; i++) part[i] = 0;
-  for (int i = 0; i < cs.n; i++) {
-    const QCon<T>& c = cs.c[i];
-    T jar[4];
-    jbq_rows(jar, c.ww, mu, c.ar0);
+    for (int q = 0; q < 8; q++) {
+      Gx[q] = Wxx * c.Jx[q] + Wxz * c.Jz[q];
+      Gy[q] = Wyy * c.Jy[q] + Wyz * c.Jz[q];
+      Gz[q] = Wxz * c.Jx[q] + Wyz * c.Jy[q] + Wzz * c.Jz[q];
+    }
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (!(jar[r] < (T)0)) continue;
-      T ew[3] = {r == 2 ? -mu : (r == 3 ? mu : (T)0), r == 0 ? mu : (r == 1 ? -mu : (T)0), (T)1}, e[3], j6[6];
-      mulMTV(e, Rw, ew);
-      j6[0] = e[0]; j6[1] = e[1]; j6[2] = e[2];
-      cross3(j6 + 3, c.x, e);
-      T d = c.D;
+    for (int p = 0; p < 6; p++) {
+      out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
 #pragma unroll
-      for (int p = 0; p < 6; p++) {
-        T dp = d * j6[p];
+      for (int q = 0; q <= p; q++) part[JBQ_TRI(p, q)] += c.Jx[p] * Gx[q] + c.Jy[p] * Gy[q] + c.Jz[p] * Gz[q];
+    }
+    const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
+    T hA[7], hB[8];      // H[A][0..5], H[A][A]; H[B][0..5], H[B][A], H[B][B]
 #pragma unroll
-        for (int q = 0; q <= p; q++) part[JBQ_TRI(p, q)] += dp * j6[q];
-      }
-      T jja = dot3(c.ja, e), jjb = dot3(c.jb, e);
-      if (c.kind == QK_ROTOR) {
-        part[27] += d * jja * jja;
+    for (int q = 0; q < 7; q++) hA[q] = c.Jx[6] * Gx[q] + c.Jy[6] * Gy[q] + c.Jz[6] * Gz[q];
 #pragma unroll
-        for (int p = 0; p < 6; p++) part[21 + p] += d * jja * j6[p];
-      } else {
-        H.aa += d * jja * jja; H.ab += d * jja * jjb; H.bb += d * jjb * jjb;
+    for (int q = 0; q < 8; q++) hB[q] = c.Jx[7] * Gx[q] + c.Jy[7] * Gy[q] + c.Jz[7] * Gz[q];
+    if (c.kind == QK_ROTOR) {
+      out7[6] += gA;
 #pragma unroll
-        for (int p = 0; p < 6; p++) { H.ca[p] += d * jja * j6[p]; H.cb[p] += d * jjb * j6[p]; }
-      }
+      for (int q = 0; q < 6; q++) part[21 + q] += hA[q];
+      part[27] += hA[6];
+    } else {
+      *fla += gA; *flb += gB;
+#pragma unroll
+      for (int q = 0; q < 6; q++) { H.ca[q] += hA[q]; H.cb[q] += hB[q]; }
+      H.aa += hA[6]; H.ab += hB[6]; H.bb += hB[7];
     }
   }
+  return mask;
 }
 
 // this lane's part of phi'(alpha) - (g1 + alpha g2) and of phi''(alpha) - g2; returns the active mask at alpha
@@ -544,8 +541,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   {
     T a2h[3] = {LL(L_A2), LL(L_A2 + 1), LL(L_A2 + 2)}, p2h[3] = {LL(L_P2), LL(L_P2 + 1), LL(L_P2 + 2)};
     T sa, ca, sb, cb;
-    jb_sincos(s.qa, &sa, &ca);
-    jb_sincos(s.qb, &sb, &cb);
+    jb_sincos_small(s.qa, &sa, &ca);
+    jb_sincos_small(s.qb, &sb, &cb);
     T R1[9], R2[9], R12[9];
     rodrigues(R1, a1, sa, ca);
     rodrigues(R2, a2h, sb, cb);
@@ -783,30 +780,38 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       a.r[0] = lr[0]; a.r[1] = lr[1]; a.r[2] = lr[2]; a.r[3] = s.wr[3]; a.r[4] = s.wr[4]; a.r[5] = s.wr[5];
       a.la = s.wla; a.lb = s.wlb; a.mo = s.wmo;
     }
-    QVec<T> Ma, res;
+    QVec<T> Ma, grad;
     qarrow_mul(cm, Ma, Mx, a);
-    jbq_eval_ww(cs, fr.Rw, a);
+    jbq_apply_all(cs, a, 0);
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
-    T f7[8], fla, flb;
-    uint32_t mask = jbq_forces(cs, fr.Rw, mu, f7, &fla, &flb);
-    cm.sumN(f7, 7);
-    QVec<T> grad = Ma;
-    qv_axpy(grad, (T)-1, fs);
-#pragma unroll
-    for (int i = 0; i < 6; i++) grad.r[i] -= f7[i];
-    grad.la -= fla; grad.lb -= flb; grad.mo -= f7[6];
     const int maxit = JbEps<T>::newton_iters();
-    bool done = !has_con;
-#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 3      /* timing experiments only: warm-start selection, no Newton loop */
-    done = true; a.r[0] += grad.r[0] + grad.la;
-#endif
-    while (cm.loop_any(!done)) {           // CTA- or warp-uniform trip count (Comm decides)
+    bool done = !has_con, full_prev = false;
+    uint32_t mask_prev = 0xffffffffu;
+    // Each trip: (1) forces + Hessian terms at the current point, gradient, convergence test; (2) Newton direction;
+    // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution.
+    for (;;) {
+      QArrow<T> H = Mx;
+      T part[28], f8[8], fla, flb;
+      const uint32_t mask = jbq_forces_hessian(cs, mu, f8, &fla, &flb, H, part);
+      T f9[9];
+#pragma unroll
+      for (int i = 0; i < 7; i++) f9[i] = f8[i];
+      f9[7] = mask == mask_prev ? (T)0 : (T)1;
+      grad = Ma;
+      qv_axpy(grad, (T)-1, fs);
+      grad.la -= fla; grad.lb -= flb;                 // leg entries are lane-local: their norm rides in the same reduce
+      f9[8] = qv_dot_leg(grad, grad);
+      cm.sumN(f9, 9);
+#pragma unroll
+      for (int i = 0; i < 6; i++) grad.r[i] -= f9[i];
+      grad.mo -= f9[6];
+      f8[7] = f9[7];
+      const T gn = scale * jb_sqrt(f9[8] + qv_dot_rep(grad, grad));
+      if (!done && iters > 0 && ((full_prev && f8[7] == (T)0) || gn < JbEps<T>::newton_tol() || iters >= maxit)) done = true;
+      if (!cm.loop_any(!done)) break;        // CTA- or warp-uniform trip count (Comm decides)
 #ifdef JBQ_DEBUG_COUNT
       if (lane == 0) g_jbq_newton_trips++;
 #endif
-      QArrow<T> H = Mx;
-      T part[28];
-      jbq_hessian(H, part, cs, fr.Rw, mu);
       cm.phase_sync(8);
       qarrow_factor<T, Comm>(cm, H, part);
       cm.phase_sync(9);
@@ -815,19 +820,11 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #pragma unroll
       for (int i = 0; i < 6; i++) search.r[i] = -search.r[i];
       search.la = -search.la; search.lb = -search.lb; search.mo = -search.mo;
-#if defined(JBQ_STOP_AFTER) && JBQ_STOP_AFTER == 4      /* timing experiments only: one Hessian + factor + solve */
-      a.r[0] += search.r[0] + search.la; done = true;
-      continue;
-#endif
       QVec<T> Mv;
       qarrow_mul(cm, Mv, Mx, search);
-      for (int i = 0; i < cs.n; i++) {
-        T u[3];
-        jbq_J_apply(u, cs.c[i], search);
-        mulMV(cs.c[i].jv, fr.Rw, u);
-      }
+      jbq_apply_all(cs, search, 1);
       cm.phase_sync(10);
-      res = Ma; qv_axpy(res, (T)-1, fs);
+      QVec<T> res = Ma; qv_axpy(res, (T)-1, fs);
       // g1 = s.(Ma - fs), g2 = s.Mv, d0 = s.grad (= phi'(0)); at alpha = 1: contact part of phi' and phi''
       T red[6];
       red[0] = qv_dot_leg(search, res); red[1] = qv_dot_leg(search, Mv); red[2] = qv_dot_leg(search, grad);
@@ -867,7 +864,9 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           }
         }
       }
-      if (done || !descent) alpha = 0;
+      if (!done && !descent) done = true;
+      if (done) alpha = 0;
+      else iters++;
       cm.phase_sync(11);
       qv_axpy(a, alpha, search);
       qv_axpy(Ma, alpha, Mv);
@@ -875,32 +874,16 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         QCon<T>& c = cs.c[i];
         c.ww[0] += alpha * c.jv[0]; c.ww[1] += alpha * c.jv[1]; c.ww[2] += alpha * c.jv[2];
       }
-      T f8[8];
-      uint32_t newmask = jbq_forces(cs, fr.Rw, mu, f8, &fla, &flb);
-      f8[7] = newmask == mask ? (T)0 : (T)1;
-      mask = newmask;
-      cm.sumN(f8, 8);
-      grad = Ma;
-      qv_axpy(grad, (T)-1, fs);
-#pragma unroll
-      for (int i = 0; i < 6; i++) grad.r[i] -= f8[i];
-      grad.la -= fla; grad.lb -= flb; grad.mo -= f8[6];
-      T gl = qv_dot_leg(grad, grad);
-      gl = cm.sum(gl);
-      const T gn = scale * jb_sqrt(gl + qv_dot_rep(grad, grad));
-      if (!done) {
-        if (descent) iters++;
-        if (!descent || (full && f8[7] == (T)0) || gn < JbEps<T>::newton_tol() || iters >= maxit) done = true;
-      }
+      mask_prev = mask; full_prev = full;
     }
-    // constraint force at the solution: f_c = f_s-residual form, f_c = M a - f_s - grad
+    // constraint force at the solution: f_c = M a - f_s - grad
     fcon = Ma;
     qv_axpy(fcon, (T)-1, fs); qv_axpy(fcon, (T)-1, grad);
   }
   JBQ_TICK(6);
   if (iter_accum) *iter_accum += iters;
   if (ncon_accum) *ncon_accum += ncon;
-  if (overflow_accum) *overflow_accum += cm.isum(cs.overflow);
+  if (overflow_accum) *overflow_accum += cs.overflow;          // per lane; the caller sums
 
   // ---------------- semi-implicit Euler, implicit in joint damping: (M + hB) a' = f_s + f_c  (mj_Euler)
   QVec<T> aeu;
@@ -936,7 +919,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     T ang = 0;
     if (wn >= (T)1e-15) { ax[0] = s.w[0] / wn; ax[1] = s.w[1] / wn; ax[2] = s.w[2] / wn; ang = h * wn; }
     T sh, ch;
-    jb_sincos((T)0.5 * ang, &sh, &ch);
+    jb_sincos_small((T)0.5 * ang, &sh, &ch);
     T q[4] = {s.quat[0], s.quat[1], s.quat[2], s.quat[3]};
     T dq[4] = {ch, ax[0] * sh, ax[1] * sh, ax[2] * sh};
     s.quat[0] = q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2] - q[3] * dq[3];

@@ -218,6 +218,7 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   const int bad = cm.isum(state_bad(s) ? 1 : 0);
   if (bad) do_reset(P, d, e, lane, s, tg, task, live);
   if (!live) return;
+  if (overflow) atomicAdd(&d.counters[3], (unsigned long long)overflow);     // rare: any lane that ran out of slots
   store_state(d, e, lane, s);
   if (lane == 0) {
     int sc = bad ? 0 : d.step_count[e] + 1;
@@ -228,7 +229,6 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
     if (a.step_type) a.step_type[e] = st;
     atomicAdd(&d.counters[1], (unsigned long long)iters);
     atomicAdd(&d.counters[2], (unsigned long long)ncon_sum);
-    if (overflow) atomicAdd(&d.counters[3], (unsigned long long)overflow);
     if (bad) atomicAdd(&d.counters[4], 1ull);
     if (e == 0) atomicAdd(&d.counters[0], (unsigned long long)d.n_sub * (unsigned long long)N);
   }

@@ -129,7 +129,7 @@ int run(const T* P, T* qpos, T* qvel, T* warm, T ctrl, int nsub, int fwd, int* n
       return -1;
   }
   if (ncon_out) *ncon_out = J.ncon[0];
-  if (ovf_out) *ovf_out = J.ovf[0];
+  if (ovf_out) *ovf_out = J.ovf[0] + J.ovf[1] + J.ovf[2] + J.ovf[3];
   if (geom_out) {
     int n = 0;
     for (int i = 0; i < 4 * JBQ_CAP; i++) if (J.rgeom[i] >= 0) { geom_out[n] = J.rgeom[i]; dist_out[n] = J.rdist[i]; n++; }
