@@ -46,6 +46,15 @@ def _flop_model():
         return {"per_substep": 7376.0, "per_newton_iteration": 1948.0, "per_contact_substep": 1272.0}
 
 
+def _traffic_per_env():
+    """DRAM bytes per env per launch from the committed ncu --set full capture (profiles/r01_v7_ncu_summary.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_v7_ncu_summary.json")) as f:
+            return float(json.load(f)["dram_traffic_bytes_per_env"])
+    except Exception:
+        return None
+
+
 def _measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -276,7 +285,8 @@ def run_cuda(args):
                     "d2h_bytes_per_step": 4 * E * (env.obs_dim + 2), "steps": e2e_steps},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": which,
+                         "frac": achieved_gbs / hbm_peak,
+                         "traffic": (_traffic_per_env() * E if _traffic_per_env() else None), "peak_source": which,
                          "note": "kernel is FP32-issue bound by design (50 sub-steps fused on chip); see fp32"},
             "fp32": {"achieved": achieved_tf, "peak": fp32_peak.value, "unit": "TFLOP/s",
                      "frac": achieved_tf / fp32_peak.value if fp32_peak.value else None,
