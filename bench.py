@@ -187,7 +187,15 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E = args.envs
-    env = BatchedJitterbugEnv(TASK, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E)
+    extra = {}
+    if args.workload == "augmented":
+        # BASELINE.json config 4: per-env randomised model parameters (legs + mass, the reference training script's
+        # defaults, benchmark.py:129-136).  A population of `--models` augmented models is compiled on the host and
+        # assigned to envs by global env id; every env's model is staged in shared memory by the kernel.
+        from jitterbug_b200 import augmented_jitterbug
+        pop = augmented_jitterbug.make_models(args.models, seed=args.seed)
+        extra = dict(models=pop, model_index=(np.arange(E, dtype=np.int64) + rank * E) % args.models)
+    env = BatchedJitterbugEnv(TASK, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4
     acts = [torch.rand(E, device=dev, generator=g) * 2 - 1 for _ in range(n_act)]
@@ -273,7 +281,9 @@ def run_cuda(args):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{TASK}, uniform random actions, {E} envs per GPU x {world} GPU, 50 sub-steps + "
-                                   f"reward + obs per step, episodes of 1000 steps with in-kernel auto-reset",
+                                   f"reward + obs per step, episodes of 1000 steps with in-kernel auto-reset"
+                                   + (f", per-env augmented models (population {args.models})"
+                                      if args.workload == "augmented" else ""),
                        "envs_per_gpu": E, "task": TASK, "l2_policy": "inputs larger than L2 "
                        f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per step vs 126 MB L2)"
                        if BYTES_PER_ENV_STEP * E > 126e6 else "inputs smaller than L2 (compute-bound kernel)",
@@ -310,6 +320,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--workload", default="shared", choices=["shared", "augmented"],
+                    help="shared: one model (headline); augmented: per-env randomised models (config 4)")
+    ap.add_argument("--models", type=int, default=256, help="augmented: size of the model population")
     ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -42,6 +42,10 @@ typedef struct {
  * augmented_jitterbug.py:95-267).  `task_ids_host`: num_envs task ids (JB_TASK_*), or NULL for all move_from_origin. */
 int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
                   const int32_t* task_ids_host);
+/* Same with a population of n_models distinct models and a per-env index into it (model_index_host[num_envs]); the
+ * per-env array is expanded on the device, so the host never holds num_envs models (config 4: 1 Mi augmented envs). */
+int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
+                          const int32_t* model_index_host, const int32_t* task_ids_host);
 void jb_sim_destroy(JbSim* sim);
 
 /* Replaces control.Environment.reset() -> task.initialize_episode (jitterbug.py:601-666) + get_observation.

@@ -25,6 +25,8 @@ class JbSimConfig(C.Structure):
 _P = C.c_void_p
 SYMBOLS = {
     "jb_sim_create": (C.c_int, [C.POINTER(_P), C.POINTER(JbSimConfig), C.POINTER(JbModelF), C.c_int, C.POINTER(C.c_int32)]),
+    "jb_sim_create_indexed": (C.c_int, [C.POINTER(_P), C.POINTER(JbSimConfig), C.POINTER(JbModelF), C.c_int,
+                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "jb_sim_destroy": (None, [_P]),
     "jb_sim_reset": (C.c_int, [_P, _P, _P, _P]),
     "jb_sim_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),

@@ -59,14 +59,15 @@ class BatchedJitterbugEnv:
         seed: Philox key for reset randomisation; streams are keyed by global env id (``env_id_offset + i``).
         random_pose / time_limit / control_timestep: the reference factory kwargs (jitterbug.py:73-79, :374-380).
         xml / model: MJCF text or a pre-compiled :class:`mjcf.CompiledModel`; default = packaged jitterbug.xml.
-        models: optional sequence of N compiled models (per-env augmented Jitterbugs).
+        models: optional sequence of compiled models (per-env augmented Jitterbugs): either N models, or K models
+            together with ``model_index`` (N ints in [0, K)) assigning one of them to every env.
     """
 
     def __init__(self, task: Union[str, Sequence] = "move_from_origin", num_envs: int = 1, device="cuda:0", seed: int = 0,
                  random_pose: bool = True, time_limit: float = DEFAULT_TIME_LIMIT,
                  control_timestep: float = DEFAULT_CONTROL_TIMESTEP, xml: Optional[str] = None,
                  model: Optional[mjcf.CompiledModel] = None, models: Optional[Sequence] = None,
-                 env_id_offset: int = 0):
+                 model_index: Optional[Sequence[int]] = None, env_id_offset: int = 0):
         self._lib = _native.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedJitterbugEnv needs a CUDA device (no CPU fallback)")
@@ -87,15 +88,21 @@ class BatchedJitterbugEnv:
         self.task_ids = np.array([TASK_ID[t] for t in names], dtype=np.int32)
         self.obs_dim = max(OBS_DIM[t] for t in set(names))
 
+        index_ptr = None
         if models is not None:
-            if len(models) != self.num_envs:
-                raise ValueError("len(models) must equal num_envs")
+            if model_index is None and len(models) != self.num_envs:
+                raise ValueError("len(models) must equal num_envs (or pass model_index)")
             self.model = models[0]
-            structs = (JbModelF * self.num_envs)()
+            structs = (JbModelF * len(models))()
             for i, cm in enumerate(models):
                 structs[i] = cm if isinstance(cm, JbModelF) else fill_struct(flatten_model(cm))
-            model_ptr, n_models = structs, self.num_envs
+            model_ptr, n_models = structs, len(models)
             timestep = float(structs[0].timestep)
+            if model_index is not None:
+                self.model_index = np.ascontiguousarray(model_index, dtype=np.int32)
+                if self.model_index.shape != (self.num_envs,):
+                    raise ValueError("model_index must have num_envs entries")
+                index_ptr = self.model_index.ctypes.data_as(C.POINTER(C.c_int32))
         else:
             self.model = model if model is not None else mjcf.compile_xml(xml)
             self._struct = fill_struct(flatten_model(self.model))
@@ -112,8 +119,9 @@ class BatchedJitterbugEnv:
         cfg = _native.JbSimConfig(self.num_envs, self.device.index or 0, self.n_sub_steps, self.step_limit,
                                   int(bool(random_pose)), self.obs_dim, int(seed) & (2 ** 64 - 1), int(env_id_offset), 0)
         self._h = C.c_void_p()
-        _native.check(self._lib.jb_sim_create(C.byref(self._h), C.byref(cfg), C.cast(model_ptr, C.POINTER(JbModelF)),
-                                              n_models, self.task_ids.ctypes.data_as(C.POINTER(C.c_int32))))
+        _native.check(self._lib.jb_sim_create_indexed(
+            C.byref(self._h), C.byref(cfg), C.cast(model_ptr, C.POINTER(JbModelF)), n_models, index_ptr,
+            self.task_ids.ctypes.data_as(C.POINTER(C.c_int32))))
         with torch.cuda.device(self.device):
             self._obs = torch.zeros(self.num_envs, self.obs_dim, device=self.device, dtype=torch.float32)
             self._reward = torch.zeros(self.num_envs, device=self.device, dtype=torch.float32)

@@ -103,6 +103,15 @@ __global__ void jb_count_kernel(const __grid_constant__ JbDev d, int* cnt, int s
   else cnt[e] = d.step_count[e];
 }
 
+// expand a population of K packed models into the per-env array: dst[e] = src[index[e]]
+__global__ void jb_expand_models_kernel(float* dst, const float* src, const int* index, int N) {
+  const int e = blockIdx.x;
+  const float* sp = src + (size_t)index[e] * JBP_SIZE;
+  float* dp = dst + (size_t)e * JBP_SIZE;
+  for (int i = threadIdx.x; i < JBP_SIZE; i += blockDim.x) dp[i] = sp[i];
+  (void)N;
+}
+
 // FP32 FMA-pipe peak: 16 independent FFMA chains per thread, enough CTAs to fill the chip (roofline denominator
 // for this compute-bound path; MEASURED_PEAKS.json only carries HBM and tensor numbers).
 __global__ void jb_fma_peak_kernel(float* out, int iters, float a, float b) {
@@ -130,9 +139,19 @@ int jb_sim_obs_stride(const JbSim* sim) { return sim ? sim->cfg.obs_stride : 0; 
 static int grid_of(int n) { return (n + JB_BLOCK - 1) / JB_BLOCK; }
 
 int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models, const int32_t* task_ids_host) {
+  return jb_sim_create_indexed(out, cfg, models_host, n_models, nullptr, task_ids_host);
+}
+
+int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
+                          const int32_t* model_index_host, const int32_t* task_ids_host) {
   if (!out || !cfg || !models_host) return fail("jb_sim_create: null argument");
   if (cfg->num_envs <= 0) return fail("jb_sim_create: num_envs must be positive");
-  if (n_models != 1 && n_models != cfg->num_envs) return fail("jb_sim_create: n_models must be 1 or num_envs");
+  if (n_models <= 0) return fail("jb_sim_create: n_models must be positive");
+  if (!model_index_host && n_models != 1 && n_models != cfg->num_envs)
+    return fail("jb_sim_create: n_models must be 1 or num_envs (or pass a model index)");
+  if (model_index_host)
+    for (int e = 0; e < cfg->num_envs; e++)
+      if (model_index_host[e] < 0 || model_index_host[e] >= n_models) return fail("jb_sim_create: model index out of range");
   if (cfg->obs_stride < 15 || cfg->obs_stride > JB_OBS_MAX) return fail("jb_sim_create: obs_stride must be in [15, 19]");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -141,7 +160,7 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   JbSim* s = new JbSim();
   memset(s, 0, sizeof(*s));
   s->cfg = *cfg;
-  s->per_env = n_models != 1;
+  s->per_env = n_models != 1 || model_index_host != nullptr;
   const size_t N = cfg->num_envs;
   JbDev& d = s->d;
   d.N = (int)N; d.n_sub = cfg->n_sub_steps; d.step_limit = cfg->step_limit; d.random_pose = cfg->random_pose;
@@ -175,6 +194,19 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
     float* pdev = nullptr;
     CUDA_TRY(cudaMalloc(&pdev, packed.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(pdev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (model_index_host) {
+      // K distinct models + per-env index: expand on the device (the host never holds num_envs models)
+      int* idev = nullptr;
+      float* full = nullptr;
+      CUDA_TRY(cudaMalloc(&idev, N * sizeof(int)));
+      CUDA_TRY(cudaMemcpy(idev, model_index_host, N * sizeof(int), cudaMemcpyHostToDevice));
+      CUDA_TRY(cudaMalloc(&full, N * JBP_SIZE * sizeof(float)));
+      jb_expand_models_kernel<<<(unsigned)N, 128>>>(full, pdev, idev, (int)N);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaDeviceSynchronize());
+      cudaFree(idev); cudaFree(pdev);
+      pdev = full;
+    }
     d.packed = pdev;
     d.per_env = s->per_env ? 1 : 0;
     CUDA_TRY(jb_configure_kernels());

@@ -189,3 +189,36 @@ def test_mixed_task_batch():
     assert torch.isfinite(obs).all() and ((rew >= 0) & (rew <= 1)).all()
     # padded columns stay zero for the narrower tasks
     assert (obs[0::5, 15:] == 0).all() and (obs[1::5, 16:] == 0).all() and (obs[3::5, 18:] == 0).all()
+
+
+def test_vec_env_rollout_with_policy():
+    """Config 5 plumbing: auto-resetting VecEnv facade + torch MLP policy on device, episode monitor."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv
+    from jitterbug_b200.rollout import MLPPolicy, VecJitterbugEnv, rollout
+    env = BatchedJitterbugEnv("move_to_pose", num_envs=512, seed=1, time_limit=0.2)     # 20-step episodes
+    vec = VecJitterbugEnv(env)
+    torch.manual_seed(0)
+    policy = MLPPolicy(env.obs_dim).to(env.device)
+    out = rollout(vec, policy, 45)
+    assert vec.episode_count == 2 * 512 and out["episodes"]["count"] == 2 * 512
+    assert out["steps_per_s"] > 0 and 0 <= out["mean_step_reward"] <= 1
+    # after an auto-reset the env continues from a fresh episode: step counts are all 45 - 40 = 5
+    assert (env.get_step_count() == 5).all()
+
+
+def test_indexed_model_population_equals_explicit_per_env_models():
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv, augmented_jitterbug
+    pop = augmented_jitterbug.make_models(5, seed=8)
+    N = 100
+    idx = np.arange(N) % 5
+    a = BatchedJitterbugEnv("move_in_direction", num_envs=N, seed=3, models=[pop[i] for i in idx])
+    b = BatchedJitterbugEnv("move_in_direction", num_envs=N, seed=3, models=pop, model_index=idx)
+    oa, ob = a.reset().clone(), b.reset().clone()
+    assert torch.equal(oa, ob)
+    acts = torch.rand(8, N, device=a.device, generator=torch.Generator(device=a.device).manual_seed(2)) * 2 - 1
+    for k in range(8):
+        ra = [t.clone() for t in a.step(acts[k])]
+        rb = b.step(acts[k])
+        assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])

@@ -154,3 +154,41 @@ def test_task_layer_c_matches_numpy(compiled_model):
         np.testing.assert_allclose(o_c, o_np, atol=1e-12)
         assert r_c == pytest.approx(tk.get_reward(), abs=1e-12)
         assert len(o_np) == [15, 16, 19, 18, 19][ti]
+
+
+def test_constraint_solution_satisfies_optimality_conditions(compiled_model):
+    """KKT check of the oracle's Newton solution, independent of how it was reached: with f = -D*min(0, J a - aref)
+    the stationarity residual M a - qfrc_smooth - J'f vanishes and forces are non-negative (pyramidal rows)."""
+    sim = O.OracleSim(compiled_model)
+    rng = np.random.default_rng(12)
+    sim.qpos[3:7] = [np.cos(0.4), 0.01 * np.sin(0.4), -0.02 * np.sin(0.4), np.sin(0.4)]
+    sim.forward()
+    checked = 0
+    for cs in range(25):
+        sim.d.ctrl[0] = rng.uniform(-1, 1)
+        for k in range(50):
+            sim.physics_step()
+            # after physics_step the data holds the position/velocity stage of the NEW state; run the acceleration
+            # stage on it without integrating
+            q, v, w = sim.qpos.copy(), sim.qvel.copy(), sim.warmstart.copy()
+            ctrl = sim.d.ctrl[0]
+            probe = O.OracleSim(compiled_model)
+            probe.set_state(q, v, w, ctrl=ctrl)
+            probe.forward()
+            n = probe.d.nefc
+            if n == 0:
+                continue
+            J = probe.view("efc_J")[:n, :15]
+            D = probe.view("efc_D")[:n]
+            aref = probe.view("efc_aref")[:n]
+            a = probe.view("qacc")[:15]
+            M = probe.view("qM")[:15, :15]
+            jar = J @ a - aref
+            f = -D * np.minimum(jar, 0)
+            res = M @ a - probe.view("qfrc_smooth")[:15] - J.T @ f
+            scale = np.abs(M @ a).max() + np.abs(J.T @ f).max()
+            assert np.abs(res).max() < 1e-7 * scale
+            assert (f >= 0).all()
+            np.testing.assert_allclose(probe.view("efc_force")[:n], f, rtol=1e-9, atol=1e-12)
+            checked += 1
+    assert checked > 800
