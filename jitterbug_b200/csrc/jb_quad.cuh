@@ -98,9 +98,12 @@ template <typename T, typename Comm> JB_HD void qarrow_mul(Comm& cm, QVec<T>& y,
   y.la = sa; y.lb = sb; y.mo = sm;
 }
 
-// Leaf-first L'DL (MuJoCo's elimination order).  `part` (28 values or nullptr) carries this lane's additive
-// contributions to the replicated block: R[21], cm[6], mm -- the Newton Hessian's contact terms.
-template <typename T, typename Comm> JB_HD void qarrow_factor(Comm& cm, QArrow<T>& A, const T* part) {
+// Leaf-first L'DL (MuJoCo's elimination order).  The replicated block (R, cm, mm) comes in one of two forms:
+//   shares == false : every lane holds the full block (M, M + hB);
+//   shares == true  : every lane holds its additive SHARE of the block (the Newton Hessian: lane 0 carries M's block
+//                     plus its own contact terms, lanes 1-3 only their contact terms) and the quad sum forms the block.
+// Either way the per-leg Schur complements are folded into the same quad reduction.
+template <typename T, typename Comm> JB_HD void qarrow_factor(Comm& cm, QArrow<T>& A, bool shares) {
   T red[28];
   T ibb = (T)1 / A.bb;
   T lab = A.ab * ibb;
@@ -113,22 +116,29 @@ template <typename T, typename Comm> JB_HD void qarrow_factor(Comm& cm, QArrow<T
   T iaa = (T)1 / A.aa;
 #pragma unroll
   for (int i = 0; i < 6; i++) La[i] = A.ca[i] * iaa;
+  if (shares) {
 #pragma unroll
-  for (int i = 0; i < 6; i++)
+    for (int i = 0; i < 6; i++)
 #pragma unroll
-    for (int j = 0; j <= i; j++) red[JBQ_TRI(i, j)] = (part ? part[JBQ_TRI(i, j)] : (T)0) - Lb[i] * A.cb[j] - La[i] * A.ca[j];
-  if (part) {
+      for (int j = 0; j <= i; j++) red[JBQ_TRI(i, j)] = A.R[JBQ_TRI(i, j)] - Lb[i] * A.cb[j] - La[i] * A.ca[j];
 #pragma unroll
-    for (int i = 0; i < 7; i++) red[21 + i] = part[21 + i];
+    for (int i = 0; i < 6; i++) red[21 + i] = A.cm[i];
+    red[27] = A.mm;
     cm.sumN(red, 28);
 #pragma unroll
-    for (int i = 0; i < 6; i++) A.cm[i] += red[21 + i];
-    A.mm += red[27];
-  } else {
-    cm.sumN(red, 21);
-  }
+    for (int i = 0; i < 21; i++) A.R[i] = red[i];
 #pragma unroll
-  for (int i = 0; i < 21; i++) A.R[i] += red[i];
+    for (int i = 0; i < 6; i++) A.cm[i] = red[21 + i];
+    A.mm = red[27];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j <= i; j++) red[JBQ_TRI(i, j)] = -Lb[i] * A.cb[j] - La[i] * A.ca[j];
+    cm.sumN(red, 21);
+#pragma unroll
+    for (int i = 0; i < 21; i++) A.R[i] += red[i];
+  }
   A.bb = ibb; A.ab = lab; A.aa = iaa;
 #pragma unroll
   for (int i = 0; i < 6; i++) { A.cb[i] = Lb[i]; A.ca[i] = La[i]; }
@@ -394,16 +404,14 @@ template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a,
 }
 
 // One pass over this lane's contacts at the current ww: constraint forces (partial generalized force: root 6 + motor
-// partial in out7[6], leg in *fla / *flb), the Hessian terms J' W J (leg block into H, replicated block into part[28]),
-// and the active-row mask (4 bits per contact).  W = sum over active rows of D e e' has 5 distinct entries for the
+// partial in out7[6], leg in *fla / *flb), the Hessian terms J' W J (added to H: leg block, and this lane's SHARE of the
+// replicated block, see qarrow_factor), and the active-row mask (4 bits per contact).  W = sum over active rows of D e e' has 5 distinct entries for the
 // pyramid {z +- mu y, z -+ mu x}.
 template <typename T>
-JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, QArrow<T>& H, T* part) {
+JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, QArrow<T>& H) {
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 7; i++) out7[i] = 0;
-#pragma unroll
-  for (int i = 0; i < 28; i++) part[i] = 0;
   *fla = 0; *flb = 0;
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
@@ -428,7 +436,7 @@ JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T
     for (int p = 0; p < 6; p++) {
       out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
 #pragma unroll
-      for (int q = 0; q <= p; q++) part[JBQ_TRI(p, q)] += c.Jx[p] * Gx[q] + c.Jy[p] * Gy[q] + c.Jz[p] * Gz[q];
+      for (int q = 0; q <= p; q++) H.R[JBQ_TRI(p, q)] += c.Jx[p] * Gx[q] + c.Jy[p] * Gy[q] + c.Jz[p] * Gz[q];
     }
     const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
     T hA[7], hB[8];      // H[A][0..5], H[A][A]; H[B][0..5], H[B][A], H[B][B]
@@ -439,8 +447,8 @@ JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T
     if (c.kind == QK_ROTOR) {
       out7[6] += gA;
 #pragma unroll
-      for (int q = 0; q < 6; q++) part[21 + q] += hA[q];
-      part[27] += hA[6];
+      for (int q = 0; q < 6; q++) H.cm[q] += hA[q];
+      H.mm += hA[6];
     } else {
       *fla += gA; *flb += gB;
 #pragma unroll
@@ -791,8 +799,15 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution.
     for (;;) {
       QArrow<T> H = Mx;
-      T part[28], f8[8], fla, flb;
-      const uint32_t mask = jbq_forces_hessian(cs, mu, f8, &fla, &flb, H, part);
+      if (lane != 0) {                   // lane 0's share carries M's replicated block (see qarrow_factor)
+#pragma unroll
+        for (int i = 0; i < 21; i++) H.R[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) H.cm[i] = 0;
+        H.mm = 0;
+      }
+      T f8[8], fla, flb;
+      const uint32_t mask = jbq_forces_hessian(cs, mu, f8, &fla, &flb, H);
       T f9[9];
 #pragma unroll
       for (int i = 0; i < 7; i++) f9[i] = f8[i];
@@ -813,7 +828,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       if (lane == 0) g_jbq_newton_trips++;
 #endif
       cm.phase_sync(8);
-      qarrow_factor<T, Comm>(cm, H, part);
+      qarrow_factor<T, Comm>(cm, H, true);
       cm.phase_sync(9);
       QVec<T> search;
       qarrow_solve(cm, search, H, grad);
@@ -892,7 +907,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     qv_axpy(rhs, (T)1, fcon);
     QArrow<T> F = Mx;
     F.aa += h * LL(L_D1); F.bb += h * LL(L_D2); F.mm += h * g[G_DAMPM];
-    qarrow_factor<T, Comm>(cm, F, nullptr);
+    qarrow_factor<T, Comm>(cm, F, false);
     qarrow_solve(cm, aeu, F, rhs);
   }
   // ---------------- save warm start (MuJoCo coordinates).  Without contacts qacc = M^-1 f_s in MuJoCo; the Euler

@@ -8,8 +8,9 @@
 #include "jb_packed.h"
 
 #ifndef JB_BLOCK
-#define JB_BLOCK 256                 /* threads per CTA; 4 threads (one quad) per env.  One 8-warp CTA per SM with the full
-                                        255-register budget (no spills) measured best; see profiles/r01_phase_timers.md */
+#define JB_BLOCK 384                 /* threads per CTA; 4 threads (one quad) per env.  One 12-warp CTA per SM (168
+                                        registers, a few hundred bytes of spills) measured marginally ahead of 256
+                                        threads x 255 registers; see profiles/r01_phase_timers.md */
 #endif
 #define JB_ENVS_PER_BLOCK (JB_BLOCK / 4)
 

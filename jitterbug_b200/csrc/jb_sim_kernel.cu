@@ -195,10 +195,9 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
 #if JB_SYNC_SUBSTEP
     __syncthreads();            // keeps the CTA's warps in the same code region: instruction-cache lines are shared
 #endif
-    const bool on = fwd_only ? k == 0 : k < nsub;
-    QState<float> keep = s;
+    // an env that is resetting inside a stepping warp (episode boundary) just repeats zero-length sub-steps: they
+    // leave the state untouched and recompute the same warm start
     jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, fwd_only, &iters, &ncon_sum, &overflow, want_rep ? &rep : nullptr);
-    if (!on) s = keep;          // warp-mates with fewer trips idle (never happens in a lock-stepped batch)
   }
   if (a.mode == JB_MODE_CONTACTS) return;
   if (fwd_only) {
@@ -252,8 +251,20 @@ static int jb_pick_block(int N) {
     if (sms <= 0) sms = 148;
   }
   if (forced >= 32 && forced <= JB_BLOCK && forced % 32 == 0) return forced;
-  int threads = JB_BLOCK;
-  while (threads > 128 && (N + threads / 4 - 1) / (threads / 4) < sms / 2) threads >>= 1;   /* measured: 4096 envs 3.7 -> 4.5 M steps/s */
+  // minimise waves x time-per-CTA with the measured per-CTA step times (ms per control step of one resident CTA:
+  // 128 threads 0.92, 256 threads 1.10, 384 threads 1.28): large batches want the 384-thread CTA (lowest cost per env),
+  // small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs
+  const int cand[3] = {384, 256, 128};
+  const float tcta[3] = {1.28f, 1.10f, 0.92f};
+  int threads = 128;
+  float best = 1e30f;
+  for (int i = 0; i < 3; i++) {
+    if (cand[i] > JB_BLOCK) continue;
+    const int epb = cand[i] / 4;
+    const int blocks = (N + epb - 1) / epb;
+    const float cost = (float)((blocks + sms - 1) / sms) * tcta[i];
+    if (cost < best * 0.999f) { best = cost; threads = cand[i]; }
+  }
   return threads;
 }
 
