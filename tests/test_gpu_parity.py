@@ -35,7 +35,8 @@ def _free_run(env, steps, seed):
 
 
 def test_single_substep_state_parity(compiled_model):
-    """One physics sub-step from identical (qpos, qvel, warmstart, ctrl): qpos/qvel within 1e-5 relative (fp32)."""
+    """One physics sub-step from identical (qpos, qvel, warmstart, ctrl): qpos within 1e-6, qvel within 1e-5 relative
+    (fp32 kernel vs fp64 oracle; the north_star tolerance is 1e-5), active contact sets identical."""
     _need_gpu()
     O = _oracle()
     N = 512
@@ -80,10 +81,11 @@ def test_single_substep_state_parity(compiled_model):
                                 np.full(8, max(1.0, np.abs(sim.qvel[6:14]).max())),
                                 np.full(1, max(1.0, abs(sim.qvel[14])))])
         worst_v = max(worst_v, float((dv / scale).max()))
+    print(f"single sub-step: worst scaled qpos error {worst_q:.2e}, worst scaled qvel error {worst_v:.2e}, skipped {skipped}")
     assert skipped < N // 10
     assert nbad_con == 0, f"{nbad_con} envs with a different active contact set"
-    assert worst_q < 1e-5, worst_q
-    assert worst_v < 1e-4, worst_v
+    assert worst_q < 1e-6, worst_q          # north_star asks 1e-5 relative; measured 1.1e-7 on B200
+    assert worst_v < 1e-5, worst_v          # measured 7.5e-7
 
 
 def test_control_step_parity_and_reward(compiled_model):
@@ -180,3 +182,73 @@ def test_heuristic_kernel_matches_reference_policy(compiled_model):
             od = {k: obs[e, s] for k, s in lay.items()}
             ref = O.heuristic(task, od)
             assert abs(act[e] - ref) < 1e-5, (task, e, act[e], ref)
+
+
+def test_long_horizon_return_distributions(compiled_model):
+    """Beyond a few control steps trajectories are chaotic, so only distributions can agree (north_star): returns of
+    the fp32 CUDA path and of the fp64 oracle from the same initial states under (a) the same open-loop random action
+    sequences and (b) the closed-loop move_from_origin heuristic must be statistically indistinguishable."""
+    _need_gpu()
+    O = _oracle()
+    import ctypes as C
+    from scipy import stats
+    N, T = 192, 120
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=21)
+    env.reset()
+    q0, v0, w0 = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+    g = torch.Generator(device=env.device).manual_seed(3)
+    acts = torch.rand(T, N, device=env.device, generator=g) * 2 - 1
+    ret_gpu = torch.zeros(N, device=env.device)
+    for k in range(T):
+        _, r, _ = env.step(acts[k])
+        ret_gpu += r
+    ret_gpu = ret_gpu.cpu().numpy()
+    # oracle: same initial states, same action sequences, C rollout on all host threads
+    L = O.lib()
+    models = (O.JboModel * N)()
+    datas = (O.JboData * N)()
+    proto = O.make_model(compiled_model)
+    for e in range(N):
+        C.memmove(C.byref(models[e]), C.byref(proto), C.sizeof(O.JboModel))
+        L.jbo_reset_data(C.byref(models[e]), C.byref(datas[e]))
+        for i in range(16):
+            datas[e].qpos[i] = q0[e, i]
+        L.jbo_forward(C.byref(models[e]), C.byref(datas[e]))
+    a_np = np.ascontiguousarray(acts.cpu().numpy().astype(np.float64))
+    rew = np.zeros((T, N))
+    dp = C.POINTER(C.c_double)
+    import os
+    L.jbo_rollout(models, datas, N, 0, a_np.ctypes.data_as(dp), T, 50, os.cpu_count() or 1, rew.ctypes.data_as(dp), None)
+    ret_cpu = rew.sum(axis=0)
+    # (a) random policy: same distribution of returns
+    ks = stats.ks_2samp(ret_gpu, ret_cpu)
+    assert ks.pvalue > 0.01, (ks, ret_gpu.mean(), ret_cpu.mean())
+    se = np.sqrt(ret_gpu.var() / N + ret_cpu.var() / N)
+    assert abs(ret_gpu.mean() - ret_cpu.mean()) < 4 * se + 1e-3, (ret_gpu.mean(), ret_cpu.mean(), se)
+    # early steps are not yet chaotic: per-env rewards of the first control steps agree closely
+    env2 = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=21)
+    env2.reset()
+    for k in range(3):
+        _, r, _ = env2.step(acts[k])
+        assert np.quantile(np.abs(r.cpu().numpy() - rew[k]), 0.9) < 1e-4
+    # (b) closed-loop heuristic: device heuristic on the GPU vs reference-policy port on the oracle
+    M = 48
+    envh = BatchedJitterbugEnv("move_from_origin", num_envs=M, seed=33)
+    obs = envh.reset()
+    qh = envh.get_state()[0].cpu().numpy().astype(np.float64)
+    rg = torch.zeros(M, device=envh.device)
+    for k in range(T):
+        obs, r, _ = envh.step(envh.heuristic_actions(obs))
+        rg += r
+    rg = rg.cpu().numpy()
+    rc = np.zeros(M)
+    for e in range(M):
+        sim = O.OracleSim(compiled_model)
+        sim.qpos[:] = qh[e]
+        sim.forward()
+        tk = O.TaskOracle(sim, "move_from_origin")
+        for k in range(T):
+            sim.control_step(O.heuristic("move_from_origin", tk.get_observation()))
+            rc[e] += tk.get_reward()
+    ksh = stats.ks_2samp(rg, rc)
+    assert ksh.pvalue > 0.01, (ksh, rg.mean(), rc.mean())
