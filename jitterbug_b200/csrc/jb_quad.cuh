@@ -403,12 +403,10 @@ template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a,
   }
 }
 
-// One pass over this lane's contacts at the current ww: constraint forces (partial generalized force: root 6 + motor
-// partial in out7[6], leg in *fla / *flb), the Hessian terms J' W J (added to H: leg block, and this lane's SHARE of the
-// replicated block, see qarrow_factor), and the active-row mask (4 bits per contact).  W = sum over active rows of D e e' has 5 distinct entries for the
-// pyramid {z +- mu y, z -+ mu x}.
+// This lane's constraint forces at the current ww: partial generalized force (root 6 + motor partial in out7[6], leg in
+// *fla / *flb) and the active-row mask (4 bits per contact).
 template <typename T>
-JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, QArrow<T>& H) {
+JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb) {
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 7; i++) out7[i] = 0;
@@ -417,11 +415,29 @@ JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T
     const QCon<T>& c = cs.c[i];
     T jar[4];
     jbq_rows(jar, c.ww, mu, c.ar0);
-    const T a0 = jar[0] < (T)0 ? (T)1 : (T)0, a1 = jar[1] < (T)0 ? (T)1 : (T)0;
-    const T a2 = jar[2] < (T)0 ? (T)1 : (T)0, a3 = jar[3] < (T)0 ? (T)1 : (T)0;
     mask |= ((jar[0] < (T)0 ? 1u : 0u) | (jar[1] < (T)0 ? 2u : 0u) | (jar[2] < (T)0 ? 4u : 0u) | (jar[3] < (T)0 ? 8u : 0u)) << (4 * i);
-    const T f0 = -c.D * jar[0] * a0, f1 = -c.D * jar[1] * a1, f2 = -c.D * jar[2] * a2, f3 = -c.D * jar[3] * a3;
+    const T f0 = jar[0] < (T)0 ? -c.D * jar[0] : (T)0, f1 = jar[1] < (T)0 ? -c.D * jar[1] : (T)0;
+    const T f2 = jar[2] < (T)0 ? -c.D * jar[2] : (T)0, f3 = jar[3] < (T)0 ? -c.D * jar[3] : (T)0;
     const T fw0 = mu * (f3 - f2), fw1 = mu * (f0 - f1), fw2 = f0 + f1 + f2 + f3;
+#pragma unroll
+    for (int p = 0; p < 6; p++) out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
+    const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
+    if (c.kind == QK_ROTOR) out7[6] += gA;
+    else { *fla += gA; *flb += gB; }
+  }
+  return mask;
+}
+
+// Hessian terms J' W J of this lane's contacts for the active set `mask` (from jbq_forces at the same point), added to
+// H: the leg block, and this lane's SHARE of the replicated block (see qarrow_factor).  W = sum over active rows of
+// D e e' has 5 distinct entries for the pyramid {z +- mu y, z -+ mu x}.
+template <typename T>
+JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H) {
+  for (int i = 0; i < cs.n; i++) {
+    const QCon<T>& c = cs.c[i];
+    const uint32_t m4 = mask >> (4 * i);
+    const T a0 = (m4 & 1u) ? (T)1 : (T)0, a1 = (m4 & 2u) ? (T)1 : (T)0;
+    const T a2 = (m4 & 4u) ? (T)1 : (T)0, a3 = (m4 & 8u) ? (T)1 : (T)0;
     const T dm = c.D * mu;
     const T Wzz = c.D * (a0 + a1 + a2 + a3), Wyz = dm * (a0 - a1), Wxz = dm * (a3 - a2);
     const T Wyy = dm * mu * (a0 + a1), Wxx = dm * mu * (a2 + a3);
@@ -433,30 +449,24 @@ JB_HD uint32_t jbq_forces_hessian(const QConSet<T>& cs, T mu, T* out7, T* fla, T
       Gz[q] = Wxz * c.Jx[q] + Wyz * c.Jy[q] + Wzz * c.Jz[q];
     }
 #pragma unroll
-    for (int p = 0; p < 6; p++) {
-      out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
+    for (int p = 0; p < 6; p++)
 #pragma unroll
       for (int q = 0; q <= p; q++) H.R[JBQ_TRI(p, q)] += c.Jx[p] * Gx[q] + c.Jy[p] * Gy[q] + c.Jz[p] * Gz[q];
-    }
-    const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
     T hA[7], hB[8];      // H[A][0..5], H[A][A]; H[B][0..5], H[B][A], H[B][B]
 #pragma unroll
     for (int q = 0; q < 7; q++) hA[q] = c.Jx[6] * Gx[q] + c.Jy[6] * Gy[q] + c.Jz[6] * Gz[q];
 #pragma unroll
     for (int q = 0; q < 8; q++) hB[q] = c.Jx[7] * Gx[q] + c.Jy[7] * Gy[q] + c.Jz[7] * Gz[q];
     if (c.kind == QK_ROTOR) {
-      out7[6] += gA;
 #pragma unroll
       for (int q = 0; q < 6; q++) H.cm[q] += hA[q];
       H.mm += hA[6];
     } else {
-      *fla += gA; *flb += gB;
 #pragma unroll
       for (int q = 0; q < 6; q++) { H.ca[q] += hA[q]; H.cb[q] += hB[q]; }
       H.aa += hA[6]; H.ab += hB[6]; H.bb += hB[7];
     }
   }
-  return mask;
 }
 
 // this lane's part of phi'(alpha) - (g1 + alpha g2) and of phi''(alpha) - g2; returns the active mask at alpha
@@ -795,19 +805,11 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     const int maxit = JbEps<T>::newton_iters();
     bool done = !has_con, full_prev = false;
     uint32_t mask_prev = 0xffffffffu;
-    // Each trip: (1) forces + Hessian terms at the current point, gradient, convergence test; (2) Newton direction;
+    // Each trip: (1) forces at the current point, gradient, convergence test; (2) Hessian, Newton direction;
     // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution.
     for (;;) {
-      QArrow<T> H = Mx;
-      if (lane != 0) {                   // lane 0's share carries M's replicated block (see qarrow_factor)
-#pragma unroll
-        for (int i = 0; i < 21; i++) H.R[i] = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) H.cm[i] = 0;
-        H.mm = 0;
-      }
       T f8[8], fla, flb;
-      const uint32_t mask = jbq_forces_hessian(cs, mu, f8, &fla, &flb, H);
+      const uint32_t mask = jbq_forces(cs, mu, f8, &fla, &flb);
       T f9[9];
 #pragma unroll
       for (int i = 0; i < 7; i++) f9[i] = f8[i];
@@ -827,6 +829,15 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #ifdef JBQ_DEBUG_COUNT
       if (lane == 0) g_jbq_newton_trips++;
 #endif
+      QArrow<T> H = Mx;
+      if (lane != 0) {                   // lane 0's share carries M's replicated block (see qarrow_factor)
+#pragma unroll
+        for (int i = 0; i < 21; i++) H.R[i] = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) H.cm[i] = 0;
+        H.mm = 0;
+      }
+      jbq_hessian(cs, mu, mask, H);
       cm.phase_sync(8);
       qarrow_factor<T, Comm>(cm, H, true);
       cm.phase_sync(9);

@@ -222,3 +222,20 @@ def test_indexed_model_population_equals_explicit_per_env_models():
         ra = [t.clone() for t in a.step(acts[k])]
         rb = b.step(acts[k])
         assert torch.equal(ra[0], rb[0]) and torch.equal(ra[1], rb[1])
+
+
+def test_trajectory_recorder_mjdata_layout(tmp_path):
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv, recorder
+    env = BatchedJitterbugEnv("face_direction", num_envs=32, seed=6)
+    traj = recorder.record(env, env.heuristic_actions, 12, env_ids=[0, 5, 31])
+    assert traj["qpos"].shape == (13, 3, 16) and traj["qvel"].shape == (13, 3, 15)
+    assert traj["qacc_warmstart"].shape == (13, 3, 15) and traj["ctrl"].shape == (13, 3, 1)
+    assert traj["observation"].shape == (13, 3, 16)
+    np.testing.assert_allclose(traj["time"][:, 0], np.arange(13) * 0.01)
+    np.testing.assert_allclose(np.linalg.norm(traj["qpos"][:, :, 3:7], axis=-1), 1, atol=1e-5)
+    assert (traj["step_type"][0] == 0).all() and (traj["step_type"][1:] == 1).all()
+    for ext in ("npz", "mat"):
+        p = str(tmp_path / f"traj.{ext}")
+        recorder.save(p, traj)
+        assert (tmp_path / f"traj.{ext}").stat().st_size > 1000
