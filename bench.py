@@ -190,11 +190,20 @@ def run_cuda(args):
     extra = {}
     if args.workload == "augmented":
         # BASELINE.json config 4: per-env randomised model parameters (legs + mass, the reference training script's
-        # defaults, benchmark.py:129-136).  A population of `--models` augmented models is compiled on the host and
-        # assigned to envs by global env id; every env's model is staged in shared memory by the kernel.
+        # defaults, benchmark.py:129-136).  --models 0 (default): every env gets its own model, drawn and compiled on
+        # the device (Philox keyed by global env id).  --models K: a population of K models compiled on the host and
+        # assigned by global env id.  Either way each env's model is staged in shared memory by the kernel.
         from jitterbug_b200 import augmented_jitterbug
-        pop = augmented_jitterbug.make_models(args.models, seed=args.seed)
-        extra = dict(models=pop, model_index=(np.arange(E, dtype=np.int64) + rank * E) % args.models)
+        if args.models > 0:
+            pop = augmented_jitterbug.make_models(args.models, seed=args.seed)
+            extra = dict(models=pop, model_index=(np.arange(E, dtype=np.int64) + rank * E) % args.models)
+        else:
+            t_c = time.perf_counter()
+            deltas = augmented_jitterbug.sample_deltas(E, seed=args.seed, device=dev, env_id_offset=rank * E)
+            extra = dict(packed_models=augmented_jitterbug.compile_models_device(deltas))
+            torch.cuda.synchronize(dev)
+            compile_s = time.perf_counter() - t_c
+            del deltas
     env = BatchedJitterbugEnv(TASK, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4
@@ -282,7 +291,9 @@ def run_cuda(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{TASK}, uniform random actions, {E} envs per GPU x {world} GPU, 50 sub-steps + "
                                    f"reward + obs per step, episodes of 1000 steps with in-kernel auto-reset"
-                                   + (f", per-env augmented models (population {args.models})"
+                                   + ((f", per-env augmented models (population {args.models}, host-compiled)"
+                                       if args.models > 0 else
+                                       f", one augmented model per env compiled on the device ({compile_s:.2f} s)")
                                       if args.workload == "augmented" else ""),
                        "envs_per_gpu": E, "task": TASK, "l2_policy": "inputs larger than L2 "
                        f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per step vs 126 MB L2)"
@@ -322,7 +333,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--workload", default="shared", choices=["shared", "augmented"],
                     help="shared: one model (headline); augmented: per-env randomised models (config 4)")
-    ap.add_argument("--models", type=int, default=256, help="augmented: size of the model population")
+    ap.add_argument("--models", type=int, default=0,
+                    help="augmented: 0 = one device-compiled model per env; K > 0 = host-compiled population of K")
     ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -46,6 +46,10 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
  * per-env array is expanded on the device, so the host never holds num_envs models (config 4: 1 Mi augmented envs). */
 int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
                           const int32_t* model_index_host, const int32_t* task_ids_host);
+/* Same from packed models already resident on the device (jb_augment_compile's output): packed_dev holds n_models *
+ * jb_packed_model_size() floats, n_models == 1 or num_envs.  The array is copied; the caller keeps its buffer. */
+int jb_sim_create_packed(JbSim** out, const JbSimConfig* cfg, const float* packed_dev, int n_models,
+                         const int32_t* task_ids_host);
 void jb_sim_destroy(JbSim* sim);
 
 /* Replaces control.Environment.reset() -> task.initialize_episode (jitterbug.py:601-666) + get_observation.
@@ -95,6 +99,69 @@ int jb_sim_get_phase_cycles(JbSim* sim, unsigned long long* out8_host);
 /* FP32 FMA-pipe peak of `device` in TFLOP/s (FFMA-chain microbenchmark): the roofline denominator of this
  * compute-bound path.  Synchronises the device. */
 int jb_measure_fp32_peak(int device, double* tflops_out);
+
+/* ---- Batched on-device compilation of augmented Jitterbugs.  Replaces
+ * augment_Jitterbug + MuJoCo's XML compile, once per env (jitterbug_dmc/augmented_jitterbug.py:95-267): a kernel
+ * applies the perturbation to leg end points / rotor offset / densities / gear and recomputes geom and body inertias,
+ * hinge axes and mj_setConst's invweights in fp64, writing the packed float layout the step kernel consumes. */
+typedef struct { JB_GEOM_FIELDS(double) } JbGeomD;
+typedef struct { JB_MODEL_FIELDS(double, JbGeomD) } JbModelD;
+#define JB_AUG_NGEOM 22   /* slots: coreBody1, coreBody2, screw1, screw2, 4 x (upper cyl, knee, lower cyl, foot), threadMass, mass */
+#define JB_AUG_NDELTA 31  /* [0] default density, [1] coreBody1 density, [2] coreBody2 density, [3 + 6k ..] leg k: upper
+                             end offset (3), lower end offset (3), [27..29] rotor offset, [30] gear */
+typedef struct {
+  JbModelD model;                        /* the unperturbed model (root frame, fp64) */
+  double density[JB_AUG_NGEOM];
+  int follows_default[JB_AUG_NGEOM];     /* 1: the geom has no density of its own (moves with the default density) */
+} JbAugBase;
+typedef struct {                         /* augment_Jitterbug's keyword arguments (augmented_jitterbug.py:95-106) */
+  int modify_legs, modify_mass, modify_core1, modify_core2, modify_global_density, modify_gear;
+  double sd_legs[3], sd_mass_pos[3], sd_core1_density, sd_core2_density, sd_global_density, sd_gear;
+} JbAugSpec;
+/* floats per packed model */
+int jb_packed_model_size(void);
+/* deltas_dev[n][JB_AUG_NDELTA] (fp64): one Gaussian per parameter like the reference draws them (rotor y / z offsets
+ * clipped to [-0.001, 1], :218-222), Philox streams keyed by (seed, env_id_offset + env). */
+int jb_augment_sample(const JbAugSpec* spec_host, uint64_t seed, uint32_t env_id_offset, int n, double* deltas_dev,
+                      void* stream);
+/* deltas_dev[n][JB_AUG_NDELTA] -> packed_dev[n][jb_packed_model_size()]; models_dev: optional n JbModel structs (the same
+ * models in the C-ABI struct layout, for inspection) or NULL.  Synchronises the stream. */
+int jb_augment_compile(const JbAugBase* base_host, const double* deltas_dev, int n, float* packed_dev,
+                       JbModel* models_dev, void* stream);
+
+/* ---- Observation-encoder hook.  Replaces Jitterbug.encode_obs (jitterbug_dmc/jitterbug.py:927-993):
+ * the first `k_encode` observation features go through a small dense network, the remaining obs_dim - k_encode are
+ * appended unchanged (the reference's use_autoencoder15 / use_autoencoder13 modes, :957-981); k_encode == obs_dim
+ * encodes everything (:949-951).  Network = the hidden layer of the reference's tanh (denoising) auto-encoder
+ * (benchmarks/denoising_autoencoder.py:66-98, encode() :195-205) or its VAE encoder (benchmarks/VAE.py:13-46: ReLU
+ * layers, then mean and std heads; encode() :134-146 returns mean + std * eps with the std head used as is).
+ * `normalize` applies the reference's per-feature extrema scaling first (denoising_autoencoder.py:218-232).
+ * n_models > 1 averages an ensemble of identically shaped encoders (jitterbug.py:983-991). */
+enum { JB_ACT_LINEAR = 0, JB_ACT_TANH = 1, JB_ACT_RELU = 2 };
+enum { JB_ENC_NORM_NONE = 0, JB_ENC_NORM_PM1 = 1, JB_ENC_NORM_01 = 2 };
+#define JB_ENC_MAX_LAYERS 4
+#define JB_ENC_MAX_WIDTH 64
+
+typedef struct {
+  int obs_dim;                        /* features read per env */
+  int k_encode;                       /* leading features fed to the network */
+  int n_layers;                       /* dense layers, 1..JB_ENC_MAX_LAYERS */
+  int dims[JB_ENC_MAX_LAYERS + 1];    /* dims[0] == k_encode, dims[n_layers] = latent size */
+  int act[JB_ENC_MAX_LAYERS];         /* JB_ACT_* per layer (ignored on a VAE's head layer) */
+  int vae;                            /* 1: the last layer is the (mean | std) head pair, weights [dims[n-1]][2 * latent] */
+  int normalize;                      /* JB_ENC_NORM_* */
+  int n_models;                       /* ensemble size, >= 1 */
+  uint32_t env_id_offset;             /* global id of env 0 (keys the VAE noise stream, like JbSimConfig) */
+} JbEncoderDesc;
+
+/* floats per ensemble member in `params_dev`: for each layer W[in][out] row-major, then b[out]; -1 on a bad desc */
+int jb_encoder_num_params(const JbEncoderDesc* desc);
+/* floats written per env: latent + obs_dim - k_encode; -1 on a bad desc */
+int jb_encoder_out_dim(const JbEncoderDesc* desc);
+/* obs_dev[n][obs_stride] -> out_dev[n][out_stride].  params_dev: n_models * jb_encoder_num_params floats;
+ * extrema_dev: [obs_dim][2] (min, max) or NULL when normalize == JB_ENC_NORM_NONE; (seed, counter) key the VAE noise. */
+int jb_encode_obs(const JbEncoderDesc* desc, const float* params_dev, const float* extrema_dev, const float* obs_dev,
+                  int n, int obs_stride, float* out_dev, int out_stride, uint64_t seed, uint64_t counter, void* stream);
 
 int jb_sim_num_envs(const JbSim* sim);
 int jb_sim_obs_stride(const JbSim* sim);

@@ -12,7 +12,7 @@ The physics (MuJoCo's mj_step for this model) runs in hand-written CUDA kernels 
 
 from . import mjcf  # noqa: F401
 from .batched_env import BatchedJitterbugEnv, TASKS, observation_layout  # noqa: F401
-from . import jitterbug, augmented_jitterbug, suite, heuristic_policies, rollout, distributed, recorder  # noqa: F401
+from . import jitterbug, augmented_jitterbug, suite, heuristic_policies, rollout, distributed, recorder, encoder  # noqa: F401
 from .jitterbug import Jitterbug  # noqa: F401
 from .gym_wrapper import JitterbugGymEnv  # noqa: F401
 from .dm import StepType, TimeStep  # noqa: F401

@@ -12,8 +12,12 @@ Differences, all deliberate:
 * hinge axes of perturbed legs are recomputed as ``cross(v_upper, z)`` / ``cross(v_upper, v_lower)`` exactly like the
   reference, which differs from the hand-tuned axes of jitterbug.xml even at zero noise.
 
-For batched simulation, :func:`make_models` compiles a population of augmented models to hand to
-``BatchedJitterbugEnv(models=...)`` (one model per env, staged per CTA in shared memory by the kernel).
+For batched simulation there are two routes to one model per env (staged per CTA in shared memory by the kernel):
+:func:`make_models` compiles a population on the host (XML -> compile, like the reference) for
+``BatchedJitterbugEnv(models=...)``; :func:`sample_deltas` + :func:`compile_models_device` draw the same perturbations
+and redo the dependent part of the compile in one CUDA kernel, one thread per env (``jb_augment_compile``), for
+``BatchedJitterbugEnv(packed_models=...)`` -- or simply ``make_batched_env(...)``.  1 Mi models take a fraction of a
+second on the device against hours of host compiles.
 """
 
 import xml.etree.ElementTree as ET
@@ -119,6 +123,104 @@ def make_models(n, seed=0, modify_legs=True, modify_mass=True, **kwargs):
     rng = np.random.RandomState(seed)
     return [mjcf.compile_xml(augment_Jitterbug(modify_legs=modify_legs, modify_mass=modify_mass, random=rng, **kwargs))
             for _ in range(n)]
+
+
+# ---------------------------------------------------------------------------------------------- device-side compile
+# order of the perturbation vector (JB_AUG_NDELTA = 31): the order augment_Jitterbug draws its Gaussians in
+DELTA_LAYOUT = {"global_density": 0, "coreBody1_density": 1, "coreBody2_density": 2, "legs": slice(3, 27),
+                "mass_pos": slice(27, 30), "gear": 30}
+
+
+def make_aug_base(cm=None):
+    """``JbAugBase`` for the C-ABI: the unperturbed model in the device layout (fp64) + per-geom densities."""
+    from . import _native
+    from .model import fill_struct, flatten_model
+    cm = mjcf.compile_xml() if cm is None else cm
+    flat = flatten_model(cm)
+    base = _native.JbAugBase()
+    base.model = fill_struct(flat, double=True)
+    slots = [flat["g_box"][0], flat["g_box"][1], flat["g_rcyl"], flat["g_rell"]]
+    for k in range(4):
+        slots += [flat["g_ucyl"][k], flat["g_knee"][k], flat["g_lcyl"][k], flat["g_foot"][k]]
+    slots += [flat["g_mcyl"], flat["g_mell"]]
+    for i, g in enumerate(slots):
+        base.density[i] = float(cm.geom_density[g["geom_id"]])
+        base.follows_default[i] = int(cm.geom_density_default[g["geom_id"]])
+    return base
+
+
+def _spec(modify_legs=True, sd_legs=(0.003, 0.003, 0.002), modify_mass=True, sd_mass_pos=(0.0015, 0.002, 0.001),
+          modify_coreBody1=False, sd_coreBody1_density=10., modify_coreBody2=False, sd_coreBody2_density=80.,
+          modify_global_density=False, sd_global_density=200., modify_gear=False, sd_gear=0.001):
+    from . import _native
+    s = _native.JbAugSpec()
+    s.modify_legs, s.modify_mass, s.modify_core1, s.modify_core2 = map(int, (modify_legs, modify_mass, modify_coreBody1,
+                                                                             modify_coreBody2))
+    s.modify_global_density, s.modify_gear = int(modify_global_density), int(modify_gear)
+    for i in range(3):
+        s.sd_legs[i], s.sd_mass_pos[i] = float(sd_legs[i]), float(sd_mass_pos[i])
+    s.sd_core1_density, s.sd_core2_density = float(sd_coreBody1_density), float(sd_coreBody2_density)
+    s.sd_global_density, s.sd_gear = float(sd_global_density), float(sd_gear)
+    return s
+
+
+def sample_deltas(n, seed=0, device="cuda", env_id_offset=0, **augment_kwargs):
+    """Draw ``n`` perturbation vectors on the device -> float64 ``[n, 31]`` (see ``DELTA_LAYOUT``).  Keyword arguments
+    and distributions are ``augment_Jitterbug``'s; the defaults are what the reference's training script turns on
+    (legs + mass, benchmark.py:129-136).  Streams are keyed by ``env_id_offset + env`` (sharding-invariant)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native
+    lib = _native.load()
+    dev = torch.device(device)
+    out = torch.empty((n, _native.AUG_NDELTA), dtype=torch.float64, device=dev)
+    spec = _spec(**augment_kwargs)
+    with torch.cuda.device(dev):
+        _native.check(lib.jb_augment_sample(C.byref(spec), int(seed) & (2 ** 64 - 1), int(env_id_offset), n,
+                                            out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def compile_models_device(deltas, base=None, return_structs=False):
+    """``deltas [n, 31]`` float64 CUDA tensor -> packed models ``[n, jb_packed_model_size()]`` float32 on the same
+    device (input of ``BatchedJitterbugEnv(packed_models=...)``).  ``return_structs``: also return the models as a host
+    array of ``JbModelF`` structs (inspection / parity tests)."""
+    import ctypes as C
+
+    import torch
+
+    from . import _native
+    from .model import JbModelF
+    lib = _native.load()
+    if deltas.dtype != torch.float64 or deltas.dim() != 2 or deltas.shape[1] != _native.AUG_NDELTA or not deltas.is_cuda:
+        raise ValueError("deltas must be a float64 CUDA tensor [n, 31]")
+    deltas = deltas.contiguous()
+    base = make_aug_base() if base is None else base
+    n = deltas.shape[0]
+    packed = torch.empty((n, lib.jb_packed_model_size()), dtype=torch.float32, device=deltas.device)
+    structs = torch.empty((n, C.sizeof(JbModelF)), dtype=torch.uint8, device=deltas.device) if return_structs else None
+    with torch.cuda.device(deltas.device):
+        _native.check(lib.jb_augment_compile(C.byref(base), deltas.data_ptr(), n, packed.data_ptr(),
+                                             structs.data_ptr() if return_structs else None,
+                                             torch.cuda.current_stream(deltas.device).cuda_stream))
+    if not return_structs:
+        return packed
+    host = structs.cpu().numpy()
+    arr = (JbModelF * n).from_buffer_copy(host.tobytes())
+    return packed, arr
+
+
+def make_batched_env(task="move_from_origin", num_envs=1, device="cuda:0", seed=0, env_id_offset=0, augment_kwargs=None,
+                     **env_kwargs):
+    """``BatchedJitterbugEnv`` with one device-compiled augmented model per env (BASELINE config 4)."""
+    from .batched_env import BatchedJitterbugEnv
+    deltas = sample_deltas(num_envs, seed=seed, device=device, env_id_offset=env_id_offset, **(augment_kwargs or {}))
+    packed = compile_models_device(deltas)
+    del deltas
+    return BatchedJitterbugEnv(task=task, num_envs=num_envs, device=device, seed=seed, env_id_offset=env_id_offset,
+                               packed_models=packed, **env_kwargs)
 
 
 def get_model_and_assets(**augment_kwargs):

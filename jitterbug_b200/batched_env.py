@@ -61,13 +61,15 @@ class BatchedJitterbugEnv:
         xml / model: MJCF text or a pre-compiled :class:`mjcf.CompiledModel`; default = packaged jitterbug.xml.
         models: optional sequence of compiled models (per-env augmented Jitterbugs): either N models, or K models
             together with ``model_index`` (N ints in [0, K)) assigning one of them to every env.
+        packed_models: float32 CUDA tensor ``[N, jb_packed_model_size()]`` from
+            ``augmented_jitterbug.compile_models_device`` (models compiled on the device); it is copied.
     """
 
     def __init__(self, task: Union[str, Sequence] = "move_from_origin", num_envs: int = 1, device="cuda:0", seed: int = 0,
                  random_pose: bool = True, time_limit: float = DEFAULT_TIME_LIMIT,
                  control_timestep: float = DEFAULT_CONTROL_TIMESTEP, xml: Optional[str] = None,
                  model: Optional[mjcf.CompiledModel] = None, models: Optional[Sequence] = None,
-                 model_index: Optional[Sequence[int]] = None, env_id_offset: int = 0):
+                 model_index: Optional[Sequence[int]] = None, env_id_offset: int = 0, packed_models=None):
         self._lib = _native.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedJitterbugEnv needs a CUDA device (no CPU fallback)")
@@ -89,7 +91,18 @@ class BatchedJitterbugEnv:
         self.obs_dim = max(OBS_DIM[t] for t in set(names))
 
         index_ptr = None
-        if models is not None:
+        if packed_models is not None:
+            if models is not None or model is not None or xml is not None:
+                raise ValueError("packed_models excludes xml / model / models")
+            if (not packed_models.is_cuda or packed_models.dtype != torch.float32 or not packed_models.is_contiguous()
+                    or tuple(packed_models.shape) != (self.num_envs, self._lib.jb_packed_model_size())
+                    or packed_models.device != self.device):
+                raise ValueError("packed_models must be a contiguous float32 [num_envs, jb_packed_model_size()] tensor "
+                                 "on the env's device")
+            self.model = None
+            model_ptr, n_models = None, self.num_envs
+            timestep = float(packed_models[0, 0])          # G_H: the time step leads the packed layout
+        elif models is not None:
             if model_index is None and len(models) != self.num_envs:
                 raise ValueError("len(models) must equal num_envs (or pass model_index)")
             self.model = models[0]
@@ -119,9 +132,14 @@ class BatchedJitterbugEnv:
         cfg = _native.JbSimConfig(self.num_envs, self.device.index or 0, self.n_sub_steps, self.step_limit,
                                   int(bool(random_pose)), self.obs_dim, int(seed) & (2 ** 64 - 1), int(env_id_offset), 0)
         self._h = C.c_void_p()
-        _native.check(self._lib.jb_sim_create_indexed(
-            C.byref(self._h), C.byref(cfg), C.cast(model_ptr, C.POINTER(JbModelF)), n_models, index_ptr,
-            self.task_ids.ctypes.data_as(C.POINTER(C.c_int32))))
+        if packed_models is not None:
+            _native.check(self._lib.jb_sim_create_packed(
+                C.byref(self._h), C.byref(cfg), packed_models.data_ptr(), n_models,
+                self.task_ids.ctypes.data_as(C.POINTER(C.c_int32))))
+        else:
+            _native.check(self._lib.jb_sim_create_indexed(
+                C.byref(self._h), C.byref(cfg), C.cast(model_ptr, C.POINTER(JbModelF)), n_models, index_ptr,
+                self.task_ids.ctypes.data_as(C.POINTER(C.c_int32))))
         with torch.cuda.device(self.device):
             self._obs = torch.zeros(self.num_envs, self.obs_dim, device=self.device, dtype=torch.float32)
             self._reward = torch.zeros(self.num_envs, device=self.device, dtype=torch.float32)

@@ -1,6 +1,7 @@
 """Builds ``jitterbug_b200/_lib/libjbsim.so`` (CUDA, sm_100a) in-tree with nvcc.
 
-Two translation units: the fused quad-per-env step kernel and the C-ABI + utility kernels; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
+Four translation units: the fused quad-per-env step kernel, the C-ABI + utility kernels, the observation encoder and
+the on-device model compiler; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
 """
 
 from __future__ import annotations
@@ -15,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
-UNITS = ["jb_sim_kernel.cu", "jb_api.cu"]
+UNITS = ["jb_sim_kernel.cu", "jb_api.cu", "jb_encoder.cu", "jb_augment.cu"]
 # -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
 # 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

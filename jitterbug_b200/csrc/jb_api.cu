@@ -9,6 +9,7 @@
 
 static thread_local std::string g_err;
 static int fail(const std::string& msg) { g_err = msg; return 1; }
+int jb_set_error(const std::string& msg) { return fail(msg); }   // for the other translation units
 #define CUDA_TRY(x)                                                                                   \
   do {                                                                                                \
     cudaError_t e_ = (x);                                                                             \
@@ -142,27 +143,17 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
   return jb_sim_create_indexed(out, cfg, models_host, n_models, nullptr, task_ids_host);
 }
 
-int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
-                          const int32_t* model_index_host, const int32_t* task_ids_host) {
-  if (!out || !cfg || !models_host) return fail("jb_sim_create: null argument");
-  if (cfg->num_envs <= 0) return fail("jb_sim_create: num_envs must be positive");
-  if (n_models <= 0) return fail("jb_sim_create: n_models must be positive");
-  if (!model_index_host && n_models != 1 && n_models != cfg->num_envs)
-    return fail("jb_sim_create: n_models must be 1 or num_envs (or pass a model index)");
-  if (model_index_host)
-    for (int e = 0; e < cfg->num_envs; e++)
-      if (model_index_host[e] < 0 || model_index_host[e] >= n_models) return fail("jb_sim_create: model index out of range");
-  if (cfg->obs_stride < 15 || cfg->obs_stride > JB_OBS_MAX) return fail("jb_sim_create: obs_stride must be in [15, 19]");
-  int ndev = 0;
-  cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || ndev == 0) return fail("jb_sim_create: no CUDA device (this library has no CPU fallback)");
-  CUDA_TRY(cudaSetDevice(cfg->device));
+// shared tail of the creators: everything but the model.  Takes ownership of `packed_dev`.
+static int sim_create_common(JbSim** out, const JbSimConfig* cfg, const int32_t* task_ids_host, float* packed_dev,
+                             bool per_env) {
   JbSim* s = new JbSim();
   memset(s, 0, sizeof(*s));
   s->cfg = *cfg;
-  s->per_env = n_models != 1 || model_index_host != nullptr;
+  s->per_env = per_env;
   const size_t N = cfg->num_envs;
   JbDev& d = s->d;
+  d.packed = packed_dev;
+  d.per_env = per_env ? 1 : 0;
   d.N = (int)N; d.n_sub = cfg->n_sub_steps; d.step_limit = cfg->step_limit; d.random_pose = cfg->random_pose;
   d.obs_stride = cfg->obs_stride; d.seed = cfg->seed; d.env_id_offset = cfg->env_id_offset;
   CUDA_TRY(cudaMalloc(&d.qpos, 16 * N * sizeof(float)));
@@ -186,31 +177,7 @@ int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* mo
   CUDA_TRY(cudaMemset(d.counters, 0, 16 * sizeof(unsigned long long)));
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
-  {
-    // pack the model(s) into the lane-interleaved float layout the quad kernel stages in shared memory
-    const size_t nm = (size_t)n_models;
-    std::vector<float> packed(nm * JBP_SIZE);
-    for (size_t i = 0; i < nm; i++) jb_pack_model<float, JbModel>(models_host[i], packed.data() + i * JBP_SIZE);
-    float* pdev = nullptr;
-    CUDA_TRY(cudaMalloc(&pdev, packed.size() * sizeof(float)));
-    CUDA_TRY(cudaMemcpy(pdev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
-    if (model_index_host) {
-      // K distinct models + per-env index: expand on the device (the host never holds num_envs models)
-      int* idev = nullptr;
-      float* full = nullptr;
-      CUDA_TRY(cudaMalloc(&idev, N * sizeof(int)));
-      CUDA_TRY(cudaMemcpy(idev, model_index_host, N * sizeof(int), cudaMemcpyHostToDevice));
-      CUDA_TRY(cudaMalloc(&full, N * JBP_SIZE * sizeof(float)));
-      jb_expand_models_kernel<<<(unsigned)N, 128>>>(full, pdev, idev, (int)N);
-      CUDA_TRY(cudaGetLastError());
-      CUDA_TRY(cudaDeviceSynchronize());
-      cudaFree(idev); cudaFree(pdev);
-      pdev = full;
-    }
-    d.packed = pdev;
-    d.per_env = s->per_env ? 1 : 0;
-    CUDA_TRY(jb_configure_kernels());
-  }
+  CUDA_TRY(jb_configure_kernels());
   CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));
@@ -221,6 +188,63 @@ int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* mo
   CUDA_TRY(cudaMalloc(&s->s_st, N * sizeof(int32_t)));
   *out = s;
   return 0;
+}
+
+static int check_config(const JbSimConfig* cfg) {
+  if (cfg->num_envs <= 0) return fail("jb_sim_create: num_envs must be positive");
+  if (cfg->obs_stride < 15 || cfg->obs_stride > JB_OBS_MAX) return fail("jb_sim_create: obs_stride must be in [15, 19]");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) return fail("jb_sim_create: no CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(cfg->device));
+  return 0;
+}
+
+int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
+                          const int32_t* model_index_host, const int32_t* task_ids_host) {
+  if (!out || !cfg || !models_host) return fail("jb_sim_create: null argument");
+  if (cfg->num_envs <= 0) return fail("jb_sim_create: num_envs must be positive");
+  if (n_models <= 0) return fail("jb_sim_create: n_models must be positive");
+  if (!model_index_host && n_models != 1 && n_models != cfg->num_envs)
+    return fail("jb_sim_create: n_models must be 1 or num_envs (or pass a model index)");
+  if (model_index_host)
+    for (int e = 0; e < cfg->num_envs; e++)
+      if (model_index_host[e] < 0 || model_index_host[e] >= n_models) return fail("jb_sim_create: model index out of range");
+  if (int rc = check_config(cfg)) return rc;
+  const size_t N = cfg->num_envs;
+  // pack the model(s) into the lane-interleaved float layout the quad kernel stages in shared memory
+  const size_t nm = (size_t)n_models;
+  std::vector<float> packed(nm * JBP_SIZE);
+  for (size_t i = 0; i < nm; i++) jb_pack_model<float, JbModel>(models_host[i], packed.data() + i * JBP_SIZE);
+  float* pdev = nullptr;
+  CUDA_TRY(cudaMalloc(&pdev, packed.size() * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(pdev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (model_index_host) {
+    // K distinct models + per-env index: expand on the device (the host never holds num_envs models)
+    int* idev = nullptr;
+    float* full = nullptr;
+    CUDA_TRY(cudaMalloc(&idev, N * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(idev, model_index_host, N * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&full, N * JBP_SIZE * sizeof(float)));
+    jb_expand_models_kernel<<<(unsigned)N, 128>>>(full, pdev, idev, (int)N);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(idev); cudaFree(pdev);
+    pdev = full;
+  }
+  return sim_create_common(out, cfg, task_ids_host, pdev, n_models != 1 || model_index_host != nullptr);
+}
+
+int jb_sim_create_packed(JbSim** out, const JbSimConfig* cfg, const float* packed_dev, int n_models,
+                         const int32_t* task_ids_host) {
+  if (!out || !cfg || !packed_dev) return fail("jb_sim_create_packed: null argument");
+  if (n_models != 1 && n_models != cfg->num_envs) return fail("jb_sim_create_packed: n_models must be 1 or num_envs");
+  if (int rc = check_config(cfg)) return rc;
+  float* pdev = nullptr;
+  const size_t bytes = (size_t)n_models * JBP_SIZE * sizeof(float);
+  CUDA_TRY(cudaMalloc(&pdev, bytes));
+  CUDA_TRY(cudaMemcpy(pdev, packed_dev, bytes, cudaMemcpyDeviceToDevice));
+  return sim_create_common(out, cfg, task_ids_host, pdev, n_models != 1);
 }
 
 void jb_sim_destroy(JbSim* s) {

@@ -41,8 +41,13 @@ enum {
 
 #ifdef __cplusplus
 // REAL: float (product) or double (test-only host build).  Geom ids are stored as exact small integers in REAL.
+#ifdef __CUDACC__
+#define JBP_HD __host__ __device__
+#else
+#define JBP_HD
+#endif
 template <typename REAL, typename MODEL>
-static inline void jb_pack_model(const MODEL& m, REAL* p) {
+JBP_HD static inline void jb_pack_model(const MODEL& m, REAL* p) {
   for (int i = 0; i < JBP_SIZE; i++) p[i] = 0;
   p[G_H] = m.timestep; p[G_GRAV] = m.gravity; p[G_M0] = m.m0;
   for (int i = 0; i < 3; i++) { p[G_C0 + i] = m.c0[i]; p[G_PM + i] = m.pm[i]; p[G_AM + i] = m.am[i]; p[G_CM + i] = m.cm[i];

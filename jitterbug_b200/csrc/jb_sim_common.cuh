@@ -13,6 +13,12 @@
                                         threads x 255 registers; see profiles/r01_phase_timers.md */
 #endif
 #define JB_ENVS_PER_BLOCK (JB_BLOCK / 4)
+/* Per-env models in shared memory are JBP_ENV_STRIDE floats apart: 460 = 12 (mod 32), so the 8 quads of a warp, each
+ * reading 4 consecutive words (lane-interleaved constants) or one broadcast word of its own model, land on 32
+ * distinct banks; the natural stride 456 = 8 (mod 32) would make every model load a 2-way bank conflict. */
+#ifndef JBP_ENV_STRIDE
+#define JBP_ENV_STRIDE (JBP_SIZE + 4)
+#endif
 
 // HBM layout: struct-of-arrays, env index fastest: qpos[16][N] (motor angle wrapped, revolutions in rev[N]),
 // qvel[15][N], warm[15][N], target[4][N], task[N], step_count[N], episode[N], reset_next[N].  A warp holds 8 envs, so

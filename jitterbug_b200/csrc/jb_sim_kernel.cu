@@ -20,6 +20,20 @@
 #define JB_MIN_BLOCKS 1
 #endif
 
+// Phase barriers synchronise JB_SYNC_GROUPS independent groups of warps (group = warp index mod JB_SYNC_GROUPS, i.e. with
+// 4 groups the warps that share an SM sub-partition); 1 = the whole CTA.
+#ifndef JB_SYNC_GROUPS
+#define JB_SYNC_GROUPS 1
+#endif
+__device__ __forceinline__ void jb_group_sync() {
+#if JB_SYNC_GROUPS <= 1
+  __syncthreads();
+#else
+  const int w = threadIdx.x >> 5;
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + (w % JB_SYNC_GROUPS)), "r"((int)(blockDim.x / JB_SYNC_GROUPS)) : "memory");
+#endif
+}
+
 // Quad sums as xor-butterflies over lanes {l, l^1, l^2, l^3}.  The kernel keeps control flow warp-uniform around every
 // call (see jb_quad.cuh), so all 32 lanes execute each shuffle together and the full mask is legal.
 struct QuadCommGPU {
@@ -50,7 +64,7 @@ struct QuadCommGPU {
   // the same time and share its instruction-cache lines (the whole sub-step is several times the I-cache)
   __device__ __forceinline__ void phase_sync(int p) {
 #if JB_PHASE_SYNC
-    if ((JB_PHASE_SYNC >> p) & 1) __syncthreads();
+    if ((JB_PHASE_SYNC >> p) & 1) jb_group_sync();
 #endif
   }
 #ifdef JBQ_PHASE_TIMERS
@@ -150,8 +164,13 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   if (d.per_env) {
     const int e0 = blockIdx.x * epb;
     const int nenv = min(epb, d.N - e0);
-    const float* src = d.packed + (size_t)e0 * JBP_SIZE;
-    for (int i = tid; i < nenv * JBP_SIZE; i += blockDim.x) jb_smem[i] = src[i];
+    // 16-byte copies; each env's model starts JBP_ENV_STRIDE floats after the previous one (see jb_sim_common.cuh)
+    const float4* src = reinterpret_cast<const float4*>(d.packed + (size_t)e0 * JBP_SIZE);
+    float4* dst = reinterpret_cast<float4*>(jb_smem);
+    for (int i = tid; i < nenv * (JBP_SIZE / 4); i += blockDim.x) {
+      const int env = i / (JBP_SIZE / 4), off = i - env * (JBP_SIZE / 4);
+      dst[env * (JBP_ENV_STRIDE / 4) + off] = src[i];
+    }
   } else {
     for (int i = tid; i < JBP_SIZE; i += blockDim.x) jb_smem[i] = d.packed[i];
   }
@@ -159,7 +178,7 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   // Every thread of the CTA runs the whole kernel body (the quad shuffles and warp votes need full warps): padding
   // quads past the end of the batch and envs not selected by a reset mask shadow a valid env and skip all stores.
   const int e = min(e_raw, d.N - 1);
-  const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_SIZE : jb_smem;
+  const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_ENV_STRIDE : jb_smem;
   QuadCommGPU cm;
 #ifdef JBQ_PHASE_TIMERS
   for (int i = 0; i < 8; i++) cm.acc[i] = 0;
@@ -193,7 +212,7 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   trips = __reduce_max_sync(0xffffffffu, trips);
   for (int k = 0; k < trips; k++) {
 #if JB_SYNC_SUBSTEP
-    __syncthreads();            // keeps the CTA's warps in the same code region: instruction-cache lines are shared
+    jb_group_sync();            // keeps the CTA's warps in the same code region: instruction-cache lines are shared
 #endif
     // an env that is resetting inside a stepping warp (episode boundary) just repeats zero-length sub-steps: they
     // leave the state untouched and recompute the same warm start
@@ -240,7 +259,7 @@ jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
 
 // CTA size: JB_BLOCK threads (one CTA per SM) when the batch fills the GPU; for small batches (e.g. the 4096-env parity
 // configuration) smaller CTAs spread the envs over more SMs.  JBSIM_BLOCK overrides (tuning experiments).
-static int jb_pick_block(int N) {
+static int jb_pick_block(int N, int per_env) {
   static int sms = 0, forced = -1;
   if (forced < 0) {
     const char* e = getenv("JBSIM_BLOCK");
@@ -251,27 +270,31 @@ static int jb_pick_block(int N) {
     if (sms <= 0) sms = 148;
   }
   if (forced >= 32 && forced <= JB_BLOCK && forced % 32 == 0) return forced;
-  // minimise waves x time-per-CTA with the measured per-CTA step times (ms per control step of one resident CTA:
-  // 128 threads 0.92, 256 threads 1.10, 384 threads 1.28): large batches want the 384-thread CTA (lowest cost per env),
-  // small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs
-  const int cand[3] = {384, 256, 128};
-  const float tcta[3] = {1.28f, 1.10f, 0.92f};
+  // minimise waves x time-per-CTA with the measured per-CTA step times (ms per control step of one resident CTA).
+  // Shared model: 128 threads 0.92, 256 threads 1.10, 384 threads 1.28 -- large batches want the 384-thread CTA (lowest
+  // cost per env), small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs.
+  // Per-env models: every env's 1.8 KB model sits in shared memory, which comes out of the L1 that caches the contact
+  // slots in local memory, so the optimum moves to 288 threads (72 models, 130 KB): 128 threads 1.03, 256 threads 1.89,
+  // 288 threads 2.06, 384 threads 3.13.
+  const int cand[2][3] = {{384, 256, 128}, {288, 256, 128}};
+  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {2.06f, 1.89f, 1.03f}};
+  const int m = per_env ? 1 : 0;
   int threads = 128;
   float best = 1e30f;
   for (int i = 0; i < 3; i++) {
-    if (cand[i] > JB_BLOCK) continue;
-    const int epb = cand[i] / 4;
+    if (cand[m][i] > JB_BLOCK) continue;
+    const int epb = cand[m][i] / 4;
     const int blocks = (N + epb - 1) / epb;
-    const float cost = (float)((blocks + sms - 1) / sms) * tcta[i];
-    if (cost < best * 0.999f) { best = cost; threads = cand[i]; }
+    const float cost = (float)((blocks + sms - 1) / sms) * tcta[m][i];
+    if (cost < best * 0.999f) { best = cost; threads = cand[m][i]; }
   }
   return threads;
 }
 
 cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st) {
-  const int threads = jb_pick_block(d.N);
+  const int threads = jb_pick_block(d.N, d.per_env);
   const int epb = threads / 4;
-  const size_t smem = (d.per_env ? (size_t)epb * JBP_SIZE : (size_t)JBP_SIZE) * sizeof(float);
+  const size_t smem = (d.per_env ? (size_t)epb * JBP_ENV_STRIDE : (size_t)JBP_SIZE) * sizeof(float);
   const int blocks = (d.N + epb - 1) / epb;
   jb_sim_kernel<<<blocks, threads, smem, st>>>(d, a);
   return cudaGetLastError();
@@ -280,7 +303,7 @@ cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st
 cudaError_t jb_configure_kernels(void) {
   // per-env models stage JB_ENVS_PER_BLOCK packed models per CTA; opt in to as much dynamic shared memory as that needs
   // (CTAs larger than 496 threads exceed the 227 KB limit in per-env mode and are rejected at launch)
-  size_t need = (size_t)JB_ENVS_PER_BLOCK * JBP_SIZE * sizeof(float);
+  size_t need = (size_t)JB_ENVS_PER_BLOCK * JBP_ENV_STRIDE * sizeof(float);
   if (need > 227 * 1024) need = 227 * 1024;
   return cudaFuncSetAttribute(jb_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }

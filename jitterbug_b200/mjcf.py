@@ -159,6 +159,8 @@ class CompiledModel:
     geom_type: np.ndarray
     geom_bodyid: np.ndarray
     geom_contype: np.ndarray
+    geom_density: np.ndarray          # compile-time only (MuJoCo drops it); kept for the on-device augmentation
+    geom_density_default: np.ndarray  # 1 where the geom took <default><geom density>
     geom_conaffinity: np.ndarray
     geom_condim: np.ndarray
     geom_size: np.ndarray
@@ -291,7 +293,7 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
             quat = quat / np.linalg.norm(quat)
         geoms.append(dict(
             name=el.attrib.get("name", ""), type=gtype, body=bidx, size=size, pos=pos, quat=quat,
-            density=float(el.attrib.get("density", default_density)),
+            density=float(el.attrib.get("density", default_density)), density_default=int("density" not in el.attrib),
             contype=int(el.attrib.get("contype", 1)), conaffinity=int(el.attrib.get("conaffinity", 1)),
         ))
         bodies[bidx].geoms.append(len(geoms) - 1)
@@ -517,6 +519,8 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
         geom_type=np.array([g["type"] for g in geoms], dtype=np.int32),
         geom_bodyid=np.array([g["body"] for g in geoms], dtype=np.int32),
         geom_contype=np.array([g["contype"] for g in geoms], dtype=np.int32),
+        geom_density=np.array([g["density"] for g in geoms], dtype=np.float64),
+        geom_density_default=np.array([g["density_default"] for g in geoms], dtype=np.int32),
         geom_conaffinity=np.array([g["conaffinity"] for g in geoms], dtype=np.int32),
         geom_condim=np.full(ngeom, 3, dtype=np.int32),
         geom_size=np.array([g["size"] for g in geoms]),

@@ -22,11 +22,14 @@ class VecJitterbugEnv:
     the observation returned for it is the first observation of its next episode (stable-baselines convention) and its
     return / length are recorded in the on-device monitor."""
 
-    def __init__(self, env: BatchedJitterbugEnv):
+    def __init__(self, env: BatchedJitterbugEnv, encoder=None):
+        """``encoder``: optional :class:`jitterbug_b200.encoder.ObservationEncoder` applied to every observation
+        returned (the reference's ``encode_obs`` hook, jitterbug.py:927-993); ``obs_dim`` is then its output width."""
         self.env = env
         self.num_envs = env.num_envs
         self.device = env.device
-        self.obs_dim = env.obs_dim
+        self.encoder = encoder
+        self.obs_dim = env.obs_dim if encoder is None else encoder.out_dim
         self._ret = torch.zeros(self.num_envs, device=self.device)
         self._len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         self.episode_returns = []          # list of tensors of finished-episode returns
@@ -35,7 +38,10 @@ class VecJitterbugEnv:
     def reset(self) -> torch.Tensor:
         self._ret.zero_()
         self._len.zero_()
-        return self.env.reset()
+        return self._encode(self.env.reset())
+
+    def _encode(self, obs):
+        return obs if self.encoder is None else self.encoder(obs)
 
     def step(self, actions: torch.Tensor):
         obs, reward, step_type = self.env.step(actions)
@@ -48,7 +54,7 @@ class VecJitterbugEnv:
             self._ret[done] = 0
             self._len[done] = 0
             obs = self.env.reset(mask=done)        # masked reset kernel: new first observations in place
-        return obs, reward, done
+        return self._encode(obs), reward, done
 
     def finished_returns(self) -> torch.Tensor:
         if not self.episode_returns:

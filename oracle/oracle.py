@@ -422,3 +422,37 @@ def heuristic(task, obs, angle_threshold=np.deg2rad(20)):
     if np.linalg.norm([dx, dy]) > 0.01:
         return h_move_forward(obs)
     return h_face_direction(obs)
+
+
+# ---------------------------------------------------------------------------------------------- observation encoders
+def normalize_obs(obs, extrema, zero_one=False):
+    """denoising_autoencoder.py:218-232 (normalize_obs) and its 0..1 sibling normalize_obs01."""
+    obs, ex = np.asarray(obs, dtype=np.float64), np.asarray(extrema, dtype=np.float64)
+    u = (obs - ex[:, 0]) / (ex[:, 1] - ex[:, 0])
+    return u if zero_one else -1.0 + 2.0 * u
+
+
+def dae_encode(x, w1, b1):
+    """Hidden layer of the tanh auto-encoder: hid_layer1 = tanh(X w1 + b1) (denoising_autoencoder.py:68, :98, :195-205)."""
+    return np.tanh(np.asarray(x, dtype=np.float64) @ w1 + b1)
+
+
+def vae_encode(x, fc1, fc2, out_mean, out_std, eps):
+    """VAE.Encoder.forward (VAE.py:32-46) then VAE.encode (:134-146): z = mean + std * eps, std head used as is.
+    Each layer is (W[in, out], b[out])."""
+    h = np.maximum(np.asarray(x, dtype=np.float64) @ fc1[0] + fc1[1], 0.0)
+    h = np.maximum(h @ fc2[0] + fc2[1], 0.0)
+    return (h @ out_mean[0] + out_mean[1]) + (h @ out_std[0] + out_std[1]) * eps
+
+
+def encode_obs(obs, encode, k_encode=None, extrema=None, zero_one=False):
+    """Jitterbug.encode_obs (jitterbug.py:927-993) for one flat observation: normalise (if extrema are given), encode the
+    first k features with ``encode`` (a callable or a list of callables = use_several_autoencoders, averaged :983-991),
+    append the rest unchanged (:957-981)."""
+    v = np.asarray(obs, dtype=np.float64)
+    if extrema is not None:
+        v = normalize_obs(v, extrema, zero_one)
+    k = len(v) if k_encode is None else k_encode
+    encs = encode if isinstance(encode, (list, tuple)) else [encode]
+    z = sum(e(v[:k]) for e in encs) / len(encs)
+    return np.concatenate([z, v[k:]])

@@ -140,3 +140,30 @@ def heuristic(task, obs):
     L.hq_heuristic.restype = C.c_float
     o = np.zeros(19, dtype=np.float32); o[:len(obs)] = obs
     return float(L.hq_heuristic(C.c_int(task), o.ctypes.data_as(C.c_void_p)))
+
+
+# ------------------------------------------------------------------------------------------------ model compiler
+_ASO = os.path.join(_HERE, "libaugsim.so")
+_ASRC = [os.path.join(_HERE, "augsim.cpp")] + [os.path.join(_HERE, "..", "..", "jitterbug_b200", "csrc", f)
+                                                for f in ("jb_augment.cuh", "jb_packed.h", "jb_model.h")] + \
+    [os.path.join(_HERE, "..", "..", "include", "jbsim.h")]
+_alib = None
+
+
+def augment(base, deltas):
+    """Host build of the device model compiler: deltas [n, 31] -> (packed f32 [n, P], JbModelF array, JbModelD array)."""
+    global _alib
+    from jitterbug_b200 import _native
+    if _alib is None:
+        if not os.path.exists(_ASO) or os.path.getmtime(_ASO) < max(os.path.getmtime(s) for s in _ASRC):
+            subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++14", "-ffp-contract=off",
+                                   "-o", _ASO, _ASRC[0]])
+        _alib = C.CDLL(_ASO)
+        assert _alib.ha_sizeof_base() == C.sizeof(_native.JbAugBase)
+    d = np.ascontiguousarray(deltas, dtype=np.float64)
+    n = d.shape[0]
+    packed = np.zeros((n, qlib().hq_packed_size()), dtype=np.float32)
+    mf = (jbmodel.JbModelF * n)()
+    md = (jbmodel.JbModelD * n)()
+    _alib.ha_augment(C.byref(base), d.ctypes.data_as(C.c_void_p), C.c_int(n), packed.ctypes.data_as(C.c_void_p), mf, md)
+    return packed, mf, md
