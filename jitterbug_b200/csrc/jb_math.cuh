@@ -36,6 +36,30 @@ JB_HD void jb_sincos_small(float x, float* s, float* c) {
   }
 }
 JB_HD void jb_sincos_small(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+// sin / cos for the angles of the sub-step (hinge angles, the wrapped motor angle, the half rotation increment): quadrant
+// reduction x = q pi/2 + r with a two-constant Cody-Waite split (exact for |q| < 2^10), then the classic single-precision
+// kernels on |r| <= pi/4 (errors ~1 ulp).  A few dozen branch-free instructions; the library call and its Payne-Hanek
+// slow path (bulky in the instruction stream of a kernel that is instruction-fetch bound) stay only for |x| > 100.
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__ void jb_sincos_far(float x, float* s, float* c) { jb_sincos(x, s, c); }
+#else
+static inline void jb_sincos_far(float x, float* s, float* c) { jb_sincos(x, s, c); }
+#endif
+JB_HD void jb_sincos_fast(float x, float* s, float* c) {
+  if (fabsf(x) > 100.f) { jb_sincos_far(x, s, c); return; }
+  const float q = rintf(x * 0.63661977236758134308f);
+  float r = fmaf(q, -1.57079625129699707031f, x);
+  r = fmaf(q, -7.54978941586159635335e-08f, r);
+  const float r2 = r * r;
+  const float sp = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+  const float cp = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                        fmaf(r2, -0.5f, 1.0f));
+  const int n = (int)q;
+  const float ss = (n & 1) ? cp : sp, cc = (n & 1) ? sp : cp;
+  *s = (n & 2) ? -ss : ss;
+  *c = ((n + 1) & 2) ? -cc : cc;
+}
+JB_HD void jb_sincos_fast(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 template <typename T> JB_HD T jb_max(T a, T b) { return a > b ? a : b; }
 template <typename T> JB_HD T jb_min(T a, T b) { return a < b ? a : b; }
 template <typename T> struct JbEps;

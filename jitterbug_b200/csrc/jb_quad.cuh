@@ -559,8 +559,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   {
     T a2h[3] = {LL(L_A2), LL(L_A2 + 1), LL(L_A2 + 2)}, p2h[3] = {LL(L_P2), LL(L_P2 + 1), LL(L_P2 + 2)};
     T sa, ca, sb, cb;
-    jb_sincos_small(s.qa, &sa, &ca);
-    jb_sincos_small(s.qb, &sb, &cb);
+    jb_sincos_fast(s.qa, &sa, &ca);
+    jb_sincos_fast(s.qb, &sb, &cb);
     T R1[9], R2[9], R12[9];
     rodrigues(R1, a1, sa, ca);
     rodrigues(R2, a2h, sb, cb);
@@ -686,7 +686,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     bias.r[3] += t[0] + N[0]; bias.r[4] += t[1] + N[1]; bias.r[5] += t[2] + N[2];
     // rotor
     T sm, cmn, r[3], cmc[3], Imc[6], ch[3] = {g[G_CM], g[G_CM + 1], g[G_CM + 2]}, Ih[6];
-    jb_sincos(s.qm, &sm, &cmn);
+    jb_sincos_fast(s.qm, &sm, &cmn);
     rodrigues(Rm, am, sm, cmn);
     sub3(r, ch, pm); mulMV(t, Rm, r); add3(cmc, pm, t);
 #pragma unroll
@@ -803,11 +803,15 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     jbq_apply_all(cs, a, 0);
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
     const int maxit = JbEps<T>::newton_iters();
-    bool done = !has_con, full_prev = false;
+    bool done = !has_con, full_prev = false, exact = false;
     uint32_t mask_prev = 0xffffffffu;
     // Each trip: (1) forces at the current point, gradient, convergence test; (2) Hessian, Newton direction;
-    // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution.
-    for (;;) {
+    // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution --
+    // unless the step just taken was a full Newton step inside one active set (the usual case from a good warm start):
+    // the cost is quadratic there, the new gradient is exactly H s + grad = 0, and the quad is finished without
+    // another pass (`exact`).
+    for (int trip = 0;; trip++) {
+      if (trip > 0 && !cm.loop_any(!done)) break;
       T f8[8], fla, flb;
       const uint32_t mask = jbq_forces(cs, mu, f8, &fla, &flb);
       T f9[9];
@@ -823,6 +827,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       for (int i = 0; i < 6; i++) grad.r[i] -= f9[i];
       grad.mo -= f9[6];
       f8[7] = f9[7];
+      if (exact) qv_zero(grad);            // keeps the result independent of what the warp's other quads still do
       const T gn = scale * jb_sqrt(f9[8] + qv_dot_rep(grad, grad));
       if (!done && iters > 0 && ((full_prev && f8[7] == (T)0) || gn < JbEps<T>::newton_tol() || iters >= maxit)) done = true;
       if (!cm.loop_any(!done)) break;        // CTA- or warp-uniform trip count (Comm decides)
@@ -901,6 +906,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         c.ww[0] += alpha * c.jv[0]; c.ww[1] += alpha * c.jv[1]; c.ww[2] += alpha * c.jv[2];
       }
       mask_prev = mask; full_prev = full;
+      if (!done && full) { done = true; exact = true; qv_zero(grad); }
     }
     // constraint force at the solution: f_c = M a - f_s - grad
     fcon = Ma;
@@ -945,7 +951,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     T ang = 0;
     if (wn >= (T)1e-15) { ax[0] = s.w[0] / wn; ax[1] = s.w[1] / wn; ax[2] = s.w[2] / wn; ang = h * wn; }
     T sh, ch;
-    jb_sincos_small((T)0.5 * ang, &sh, &ch);
+    jb_sincos_fast((T)0.5 * ang, &sh, &ch);
     T q[4] = {s.quat[0], s.quat[1], s.quat[2], s.quat[3]};
     T dq[4] = {ch, ax[0] * sh, ax[1] * sh, ax[2] * sh};
     s.quat[0] = q[0] * dq[0] - q[1] * dq[1] - q[2] * dq[2] - q[3] * dq[3];
