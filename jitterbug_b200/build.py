@@ -1,7 +1,7 @@
 """Builds ``jitterbug_b200/_lib/libjbsim.so`` (CUDA, sm_100a) in-tree with nvcc.
 
-Four translation units: the fused quad-per-env step kernel, the C-ABI + utility kernels, the observation encoder and
-the on-device model compiler; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
+Five objects: the fused quad-per-env step kernel in its two instantiations (shared model / per-env models), the C-ABI +
+utility kernels, the observation encoder and the on-device model compiler; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
 """
 
 from __future__ import annotations
@@ -16,7 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
-UNITS = ["jb_sim_kernel.cu", "jb_api.cu", "jb_encoder.cu", "jb_augment.cu"]
+# (source, object stem, extra flags): the step kernel is instantiated twice, see the head of jb_sim_kernel.cu
+UNITS = [("jb_sim_kernel.cu", "jb_sim_kernel", []), ("jb_sim_kernel.cu", "jb_sim_kernel_perenv", ["-DJB_PER_ENV_BUILD"]),
+         ("jb_api.cu", "jb_api", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
 # -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
 # 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -49,11 +51,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-    def compile_one(unit):
-        obj = os.path.join(LIBDIR, unit.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, unit), "-o", obj]
+    def compile_one(spec):
+        unit, stem, extra = spec
+        obj = os.path.join(LIBDIR, stem + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, unit), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        log = os.path.join(LIBDIR, unit.replace(".cu", ".ptxas.log"))
+        log = os.path.join(LIBDIR, stem + ".ptxas.log")
         with open(log, "w") as f:
             f.write(r.stdout + r.stderr)
         if r.returncode != 0:

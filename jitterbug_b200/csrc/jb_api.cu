@@ -26,7 +26,9 @@ struct JbSim {
   float *s_act, *s_obs, *s_rew; int32_t* s_st;
 };
 
-static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) { return jb_launch_sim(s->d, a, st); }
+static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
+  return s->per_env ? jb_launch_sim_perenv(s->d, a, st) : jb_launch_sim(s->d, a, st);
+}
 
 #define JB_REP (4 * 8)   /* 4 lanes x JBQ_CAP staging slots per env */
 
@@ -177,7 +179,7 @@ static int sim_create_common(JbSim** out, const JbSimConfig* cfg, const int32_t*
   CUDA_TRY(cudaMemset(d.counters, 0, 16 * sizeof(unsigned long long)));
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
-  CUDA_TRY(jb_configure_kernels());
+  CUDA_TRY(per_env ? jb_configure_kernels_perenv() : jb_configure_kernels());
   CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));

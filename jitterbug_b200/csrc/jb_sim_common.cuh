@@ -45,6 +45,9 @@ struct JbLaunchArgs {
   int* rep_geom; float* rep_dist;   // CONTACTS: staging [N][4*JBQ_CAP]
 };
 
+// two instantiations of jb_sim_kernel.cu: shared model / per-env models (see the head of that file)
 cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
-cudaError_t jb_configure_kernels(void);   // per device: opt in to the dynamic shared memory the per-env mode needs
+cudaError_t jb_configure_kernels(void);
+cudaError_t jb_launch_sim_perenv(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
+cudaError_t jb_configure_kernels_perenv(void);   // per device: opt in to the dynamic shared memory the per-env mode needs
 #endif

@@ -7,6 +7,22 @@
 #include "jb_task.cuh"
 #include <stdlib.h>
 
+// This file is compiled twice (jitterbug_b200/build.py): as is for the shared-model kernel (384-thread CTAs, 168
+// registers), and with -DJB_PER_ENV_BUILD for the per-env-model kernel: there every env's 1.8 KB model is staged in shared
+// memory, which comes out of the L1 that caches the local-memory contact slots and spills, so that build trades CTA
+// size for registers (256-thread bound: ~214 registers, no spills) and runs 192-thread CTAs.
+#ifdef JB_PER_ENV_BUILD
+#undef JB_BLOCK
+#define JB_BLOCK 256
+#define JB_SIM_KERNEL jb_sim_kernel_perenv
+#define JB_LAUNCH_SIM jb_launch_sim_perenv
+#define JB_CONFIGURE jb_configure_kernels_perenv
+#else
+#define JB_SIM_KERNEL jb_sim_kernel
+#define JB_LAUNCH_SIM jb_launch_sim
+#define JB_CONFIGURE jb_configure_kernels
+#endif
+
 #ifndef JB_SYNC_SUBSTEP
 #define JB_SYNC_SUBSTEP 1
 #endif
@@ -155,7 +171,7 @@ __device__ __forceinline__ void write_obs(const float* g, const JbDev& d, int e,
 extern __shared__ float jb_smem[];
 
 __global__ void __launch_bounds__(JB_BLOCK, JB_MIN_BLOCKS)
-jb_sim_kernel(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchArgs a) {
+JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 3;
   const int epb = blockDim.x >> 2;            // envs per CTA (the CTA size is chosen at launch, <= JB_BLOCK)
@@ -273,11 +289,9 @@ static int jb_pick_block(int N, int per_env) {
   // minimise waves x time-per-CTA with the measured per-CTA step times (ms per control step of one resident CTA).
   // Shared model: 128 threads 0.92, 256 threads 1.10, 384 threads 1.28 -- large batches want the 384-thread CTA (lowest
   // cost per env), small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs.
-  // Per-env models: every env's 1.8 KB model sits in shared memory, which comes out of the L1 that caches the contact
-  // slots in local memory, so the optimum moves to 288 threads (72 models, 130 KB): 128 threads 1.03, 256 threads 1.89,
-  // 288 threads 2.06, 384 threads 3.13.
-  const int cand[2][3] = {{384, 256, 128}, {288, 256, 128}};
-  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {2.06f, 1.89f, 1.03f}};
+  // Per-env models (the JB_PER_ENV_BUILD instantiation): 128 threads 0.82, 192 threads 1.12, 256 threads 1.45.
+  const int cand[2][3] = {{384, 256, 128}, {256, 192, 128}};
+  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {1.45f, 1.12f, 0.82f}};
   const int m = per_env ? 1 : 0;
   int threads = 128;
   float best = 1e30f;
@@ -291,19 +305,19 @@ static int jb_pick_block(int N, int per_env) {
   return threads;
 }
 
-cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st) {
+cudaError_t JB_LAUNCH_SIM(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st) {
   const int threads = jb_pick_block(d.N, d.per_env);
   const int epb = threads / 4;
   const size_t smem = (d.per_env ? (size_t)epb * JBP_ENV_STRIDE : (size_t)JBP_SIZE) * sizeof(float);
   const int blocks = (d.N + epb - 1) / epb;
-  jb_sim_kernel<<<blocks, threads, smem, st>>>(d, a);
+  JB_SIM_KERNEL<<<blocks, threads, smem, st>>>(d, a);
   return cudaGetLastError();
 }
 
-cudaError_t jb_configure_kernels(void) {
+cudaError_t JB_CONFIGURE(void) {
   // per-env models stage JB_ENVS_PER_BLOCK packed models per CTA; opt in to as much dynamic shared memory as that needs
   // (CTAs larger than 496 threads exceed the 227 KB limit in per-env mode and are rejected at launch)
   size_t need = (size_t)JB_ENVS_PER_BLOCK * JBP_ENV_STRIDE * sizeof(float);
   if (need > 227 * 1024) need = 227 * 1024;
-  return cudaFuncSetAttribute(jb_sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+  return cudaFuncSetAttribute(JB_SIM_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }
