@@ -35,7 +35,10 @@
 #ifdef JBQ_DEBUG_COUNT
 static long long g_jbq_ls_iters = 0, g_jbq_newton_trips = 0;
 #endif
-#define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms) */
+#ifndef JBQ_CAP
+#define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms); the active-row
+                                           masks pack 4 bits per slot into 32 bits, so 8 is also the most they hold */
+#endif
 #define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
 template <typename T> struct QState {

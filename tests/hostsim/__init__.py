@@ -88,7 +88,7 @@ def quad_substeps(packed, qpos, qvel, warm, ctrl, nsub=1, forward_only=False, wa
     real = C.c_double if double else C.c_float
     q = np.array(qpos, dtype=dt).copy(); v = np.array(qvel, dtype=dt).copy(); w = np.array(warm, dtype=dt).copy()
     ncon, ovf = C.c_int(), C.c_int()
-    geom = np.full(32, -1, dtype=np.int32); dist = np.zeros(32, dtype=dt)
+    geom = np.full(64, -1, dtype=np.int32); dist = np.zeros(64, dtype=dt)      # >= 4 * JBQ_CAP
     fn = L.hq_substeps_f64 if double else L.hq_substeps_f32
     fn.restype = C.c_int
     P = C.c_void_p

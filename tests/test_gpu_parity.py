@@ -88,6 +88,49 @@ def test_single_substep_state_parity(compiled_model):
     assert worst_v < 1e-5, worst_v          # measured 7.5e-7
 
 
+def test_many_contacts_per_lane_on_device(compiled_model):
+    """States with the core pressed into the floor (>= 12 contacts, up to 6 in the lanes that own the core boxes): the
+    lanes that own the core boxes fill 6 of their 8 contact slots.  Active sets must equal the oracle's and one sub-step
+    must agree (forces are huge here: velocities compared at 1e-4 of their scale)."""
+    _need_gpu()
+    O = _oracle()
+    N = 96
+    rng = np.random.default_rng(5)
+    qpos = np.tile(compiled_model.qpos0, (N, 1))
+    qpos[:, 2] = 0.021 - 0.004 * rng.random(N)
+    ang = 0.02 * rng.standard_normal((N, 3))
+    qpos[:, 3] = 1.0
+    qpos[:, 4:7] = 0.5 * ang
+    qpos[:, 3:7] /= np.linalg.norm(qpos[:, 3:7], axis=1, keepdims=True)
+    qvel = 0.05 * rng.standard_normal((N, 15))
+    env1 = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=1, control_timestep=0.0002, time_limit=float("inf"))
+    env1.reset()
+    env1.set_state(qpos, qvel, np.zeros((N, 15)), step_count=np.ones(N))
+    qpos, qvel, warm = [t.cpu().numpy().astype(np.float64) for t in env1.get_state()]
+    ncon, geom, dist = [t.cpu().numpy() for t in env1.contacts(32)]
+    a = torch.full((N,), 0.3, device=env1.device)
+    env1.step(a)
+    q1, v1, _ = [t.cpu().numpy().astype(np.float64) for t in env1.get_state()]
+    assert env1.counters()["contact_overflows"] == 0
+    sim = O.OracleSim(compiled_model)
+    checked = 0
+    for e in range(N):
+        sim.set_state(qpos[e], qvel[e], warm[e], ctrl=0.3)
+        sim.step1()
+        g2, d2, ex, _ = sim.contacts()
+        if any(abs(dd) < 1e-6 for dd in d2):
+            continue
+        act = [int(gg) for gg, xx in zip(g2, ex) if not xx]
+        assert [int(geom[e, i]) for i in range(ncon[e])] == act
+        assert ncon[e] >= 12
+        sim.step2()
+        np.testing.assert_allclose(q1[e], sim.qpos, atol=2e-6)
+        scale = max(1.0, np.abs(sim.qvel).max())
+        assert np.abs(v1[e] - sim.qvel).max() < 1e-4 * scale
+        checked += 1
+    assert checked > N // 2
+
+
 def test_control_step_parity_and_reward(compiled_model):
     """One control step (50 sub-steps) from identical states; reward within 1e-4, obs within 2e-3 (chaotic contact)."""
     _need_gpu()

@@ -68,3 +68,36 @@ def test_forward_only_is_a_zero_length_step(compiled_model, packed):
     np.testing.assert_allclose(q1[:3], q[:3], atol=0)
     np.testing.assert_allclose(v1, v, atol=0)
     np.testing.assert_allclose(w1, sim.warmstart, rtol=1e-6, atol=1e-5)
+
+
+def test_many_contacts_per_lane(compiled_model, packed):
+    """Core pressed into the floor: the lanes that own the core boxes carry 4 box corners + foot + lower-leg contacts
+    (6 of the 8 slots a lane has)."""
+    Pd, Pf = packed
+    sim = O.OracleSim(compiled_model)
+    rng = np.random.default_rng(5)
+    seen = 0
+    for trial in range(6):
+        q = compiled_model.qpos0.copy()
+        q[2] = 0.021 - 0.001 * trial
+        ang = 0.02 * rng.standard_normal(3)
+        q[3:7] = [1.0, *(0.5 * ang)]
+        q[3:7] /= np.linalg.norm(q[3:7])
+        v = 0.05 * rng.standard_normal(15)
+        sim.set_state(q, v, ctrl=0.3)
+        sim.forward()
+        g2, dist, excl, _ = sim.contacts()
+        if any(abs(d) < 1e-9 for d in dist):
+            continue
+        w = sim.warmstart.copy()
+        active = sorted(int(g) for g, x in zip(g2, excl) if not x)
+        sim.physics_step()
+        q1, v1, w1, it, ncon, cons, ovf = hostsim.quad_substeps(Pd, q, v, w, 0.3, 1, False, True)
+        assert ovf == 0 and [c for c, _ in cons] == active
+        assert ncon >= 12                                     # 8 box corners alone
+        np.testing.assert_allclose(q1, sim.qpos, atol=1e-12)
+        np.testing.assert_allclose(v1, sim.qvel, rtol=1e-7, atol=5e-8)
+        qf, vf, *_ = hostsim.quad_substeps(Pf, q, v, w, 0.3, 1, False, False)
+        np.testing.assert_allclose(vf, sim.qvel, rtol=2e-3, atol=2e-3)
+        seen += 1
+    assert seen >= 4
