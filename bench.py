@@ -47,9 +47,9 @@ def _flop_model():
 
 
 def _traffic_per_env():
-    """DRAM bytes per env per launch from the committed ncu --set full capture (profiles/r01_v7_ncu_summary.json)."""
+    """DRAM bytes per env per launch from the committed ncu --set full capture (profiles/r01_v8_ncu_summary.json)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_v7_ncu_summary.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01_v8_ncu_summary.json")) as f:
             return float(json.load(f)["dram_traffic_bytes_per_env"])
     except Exception:
         return None
