@@ -158,7 +158,7 @@ def run_reference(args):
         rates.append(r); times.append(dt)
     value = n_env * n_steps * len(times) / sum(times)
     sample = f"{n_env} envs x {n_steps} control steps per step, fp64 C oracle port (oracle/jb_oracle.c), {cores} pthreads"
-    print(json.dumps({
+    emit_json({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -166,7 +166,7 @@ def run_reference(args):
                                f"here: parity unpinned)", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
     return 0
 
 
@@ -317,10 +317,18 @@ def run_cuda(args):
         }
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        emit_json(out)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_FD = 1
+
+
+def emit_json(obj):
+    sys.stdout.flush()
+    os.write(_JSON_FD, (json.dumps(obj) + "\n").encode())
 
 
 def main():
@@ -338,6 +346,12 @@ def main():
     ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly one JSON line: everything else that lands on file descriptor 1 (NCCL's version banner, any
+    # library chatter) is sent to stderr, and the line itself goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)

@@ -1,4 +1,4 @@
-"""Tuning helper (GPU): distribution of contacts per lane / warp / CTA in the bench workload (one snapshot per control step)."""
+"""Tuning helper (GPU): distribution and persistence of contact load per env in the bench workload."""
 import sys
 import numpy as np
 import torch
@@ -16,26 +16,22 @@ lane_of[1], lane_of[2], lane_of[3], lane_of[4] = 0, 1, 2, 2
 for k in range(4):
     lane_of[5 + 4 * k:9 + 4 * k] = k
 lane_of[21] = lane_of[22] = 3
-hist = np.zeros(12, dtype=np.int64)
-wmax = np.zeros(12, dtype=np.int64)
-cmax = np.zeros(12, dtype=np.int64)
-emax_hist = np.zeros(33, dtype=np.int64)
-geom_hist = np.zeros(32, dtype=np.int64)
-for snap in range(20):
+T = 60
+lmax = np.zeros((T, E), dtype=np.int8)
+for t in range(T):
     env.step(torch.rand(E, device="cuda", generator=g) * 2 - 1)
-    ncon, geom, dist = [t.cpu().numpy() for t in env.contacts(32)]
+    ncon, geom, dist = [x.cpu().numpy() for x in env.contacts(32)]
     cnt = np.zeros((E, 4), dtype=np.int64)
     for j in range(32):
         gg = geom[:, j]
         ok = gg >= 0
         np.add.at(cnt, (np.nonzero(ok)[0], lane_of[gg[ok]]), 1)
-        np.add.at(geom_hist, gg[ok], 1)
-    hist += np.bincount(cnt.ravel(), minlength=12)[:12]
-    wmax += np.bincount(cnt.reshape(-1, 8 * 4).max(1), minlength=12)[:12]
-    cmax += np.bincount(cnt.reshape(-1, 96 * 4).max(1), minlength=12)[:12]
-    emax_hist += np.bincount(ncon, minlength=33)[:33]
-print("per-lane contact count histogram      ", (hist / hist.sum()).round(4))
-print("max over the 32 lanes of a warp       ", (wmax / wmax.sum()).round(4))
-print("max over the 384 lanes of a CTA       ", (cmax / cmax.sum()).round(4))
-print("contacts per env histogram            ", (emax_hist / emax_hist.sum()).round(4)[:20])
-print("contacts by geom id                   ", (geom_hist / geom_hist.sum()).round(3))
+    lmax[t] = cnt.max(1)
+print("max contacts in one lane, per env snapshot:", (np.bincount(lmax.ravel(), minlength=8)[:8] / lmax.size).round(4))
+heavy = lmax >= 2
+print("P(heavy)=", heavy.mean().round(4))
+for lag in (1, 5, 20, 50):
+    a, b = heavy[:-lag], heavy[lag:]
+    print(f"lag {lag}: P(heavy at t+lag | heavy at t) = {(a & b).sum() / max(a.sum(), 1):.3f}   P(heavy | not heavy) = {(~a & b).sum() / max((~a).sum(), 1):.3f}")
+frac = heavy.mean(0)
+print("per-env fraction of heavy snapshots, quantiles 50/90/99/99.9:", np.quantile(frac, [0.5, 0.9, 0.99, 0.999]).round(3))
