@@ -146,10 +146,7 @@ int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_hos
 }
 
 // shared tail of the creators: everything but the model.  Takes ownership of `packed_dev`.
-static int sim_create_common(JbSim** out, const JbSimConfig* cfg, const int32_t* task_ids_host, float* packed_dev,
-                             bool per_env) {
-  JbSim* s = new JbSim();
-  memset(s, 0, sizeof(*s));
+static int sim_fill(JbSim* s, const JbSimConfig* cfg, const int32_t* task_ids_host, float* packed_dev, bool per_env) {
   s->cfg = *cfg;
   s->per_env = per_env;
   const size_t N = cfg->num_envs;
@@ -188,6 +185,18 @@ static int sim_create_common(JbSim** out, const JbSimConfig* cfg, const int32_t*
   CUDA_TRY(cudaMalloc(&s->s_obs, N * cfg->obs_stride * sizeof(float)));
   CUDA_TRY(cudaMalloc(&s->s_rew, N * sizeof(float)));
   CUDA_TRY(cudaMalloc(&s->s_st, N * sizeof(int32_t)));
+  return 0;
+}
+
+extern "C" void jb_sim_destroy(JbSim* s);
+static int sim_create_common(JbSim** out, const JbSimConfig* cfg, const int32_t* task_ids_host, float* packed_dev,
+                             bool per_env) {
+  JbSim* s = new JbSim();
+  memset(s, 0, sizeof(*s));
+  s->d.packed = packed_dev;                   // owned from here on: released by jb_sim_destroy on any failure below
+  s->cfg.device = cfg->device;
+  const int rc = sim_fill(s, cfg, task_ids_host, packed_dev, per_env);
+  if (rc != 0) { jb_sim_destroy(s); return rc; }
   *out = s;
   return 0;
 }
