@@ -1,5 +1,6 @@
 // C-ABI of the batched Jitterbug simulator + the light-weight utility kernels.  See include/jbsim.h for the contract.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -27,7 +28,9 @@ struct JbSim {
 };
 
 static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
-  return s->per_env ? jb_launch_sim_perenv(s->d, a, st) : jb_launch_sim(s->d, a, st);
+  static int force256 = -1;                  // tuning: JBSIM_KERNEL=256 runs the shared model through the 256-thread build
+  if (force256 < 0) { const char* e = getenv("JBSIM_KERNEL"); force256 = (e && atoi(e) == 256) ? 1 : 0; }
+  return (s->per_env || force256) ? jb_launch_sim_perenv(s->d, a, st) : jb_launch_sim(s->d, a, st);
 }
 
 #define JB_REP (4 * 8)   /* 4 lanes x JBQ_CAP staging slots per env */
@@ -176,7 +179,8 @@ static int sim_fill(JbSim* s, const JbSimConfig* cfg, const int32_t* task_ids_ho
   CUDA_TRY(cudaMemset(d.counters, 0, 16 * sizeof(unsigned long long)));
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
-  CUDA_TRY(per_env ? jb_configure_kernels_perenv() : jb_configure_kernels());
+  CUDA_TRY(jb_configure_kernels_perenv());
+  CUDA_TRY(jb_configure_kernels());
   CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
   CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));

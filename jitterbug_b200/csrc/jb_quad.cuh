@@ -33,11 +33,18 @@
 #define JBQ_TICK(p) cm.phase_sync(p)
 #endif
 #ifdef JBQ_DEBUG_COUNT
-static long long g_jbq_ls_iters = 0, g_jbq_newton_trips = 0;
+static long long g_jbq_ls_iters = 0, g_jbq_newton_trips = 0, g_jbq_spread_moves = 0;
 #endif
 #ifndef JBQ_CAP
 #define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms); the active-row
                                            masks pack 4 bits per slot into 32 bits, so 8 is also the most they hold */
+#endif
+// JBQ_SPREAD: balance a heavy lane's leg contacts over its quad (see the leg phase of jbq_substep).  It shortens the
+// contact loops of the fullest lane from 4 to 2 trips, but costs ~800 instructions and 15 live accumulators: a gain where
+// registers are plentiful (per-env-model kernel, +10 %), a loss in the 168-register shared-model kernel (-7 %), so the
+// builds choose.  The host emulation keeps it on.
+#ifndef JBQ_SPREAD
+#define JBQ_SPREAD 1
 #endif
 #define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
 
@@ -51,7 +58,9 @@ template <typename T> struct QVec { T r[6]; T la, lb, mo; };
 template <typename T> struct QArrow {   // R, cm, mm replicated; aa..cb this lane's leg
   T R[21]; T cm[6], mm; T aa, ab, bb, ca[6], cb[6];
 };
-enum { QK_LEG = 0, QK_ROOT = 1, QK_ROTOR = 2 };
+enum { QK_LEG = 0, QK_ROOT = 1, QK_ROTOR = 2, QK_LEG_F = 3 };   // LEG_F: a contact of ANOTHER lane's leg (see jbq_spread)
+// raw candidates parked in a slot's `kind` until they are built: geom id | JBQ_TAG_LOWER | JBQ_TAG_FOREIGN
+enum { JBQ_TAG_LOWER = 256, JBQ_TAG_FOREIGN = 512 };
 template <typename T> struct QCon {
   // world-frame rows of the 3 x 8 contact Jacobian over (root lin 3, root ang 3, jA, jB): u_world = J (a_root, qA, qB)
   // with (qA, qB) = (la, lb) of this lane's leg, or (motor, -) for a rotor contact.  Row k = [r_k, x cross r_k, r_k.ja,
@@ -238,16 +247,21 @@ template <typename T> struct QBody {     // how a geom's body moves: joint colum
   const T* a1; const T* p1; T qd1;       // first joint above the body (leg hinge 1, or the motor)
   const T* a2; const T* p2; T qd2; bool lower;
   T invw;
+  bool defer;                            // park the raw contact (point, dist, geom) in its slot; jbq_build comes later
 };
 
+// Fill slot `c` for a contact at root-frame point x (on a body described by b) with penetration `dist`: Jacobian rows,
+// regulariser, reference acceleration.
+#if JBQ_SPREAD          /* the out-of-line unit is the builder (called from jbq_emit and from the spread step) ... */
+#define JBQ_BUILD_ATTR JB_COLD
+#define JBQ_EMIT_ATTR JB_HD
+#else                   /* ... or, without spreading, the whole emit as one call per contact site */
+#define JBQ_BUILD_ATTR JB_HD
+#define JBQ_EMIT_ATTR JB_COLD
+#endif
 template <typename T>
-JB_COLD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
-                    const QReport<T>* rep, int lane) {
-  if (!(dist < (T)0)) return;            // dist >= includemargin (= 0): MuJoCo excludes it from the solver
-  int i = cs.n;
-  if (i >= JBQ_CAP) { cs.overflow = 1; return; }
-  cs.n = i + 1;
-  QCon<T>& c = cs.c[i];
+JBQ_BUILD_ATTR void jbq_build(const T* g, QCon<T>& c, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
+                     const QReport<T>* rep, int lane, int i) {
   c.kind = b.kind;
   T ja[3] = {0, 0, 0}, jb[3] = {0, 0, 0}, r[3];
   if (b.kind != QK_ROOT) {
@@ -274,6 +288,21 @@ JB_COLD void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBo
   c.ar0 = -g[G_SOLK] * imp * dist;
   c.uref[0] = -g[G_SOLB] * vw[0]; c.uref[1] = -g[G_SOLB] * vw[1]; c.uref[2] = -g[G_SOLB] * vw[2];
   if (rep) { rep->geom[(lane * JBQ_CAP + i) * rep->stride] = geom; rep->dist[(lane * JBQ_CAP + i) * rep->stride] = dist; }
+}
+
+template <typename T>
+JBQ_EMIT_ATTR void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
+                    const QReport<T>* rep, int lane) {
+  if (!(dist < (T)0)) return;            // dist >= includemargin (= 0): MuJoCo excludes it from the solver
+  int i = cs.n;
+  if (i >= JBQ_CAP) { cs.overflow = 1; return; }
+  cs.n = i + 1;
+  QCon<T>& c = cs.c[i];
+  if (b.defer) {
+    c.ww[0] = x[0]; c.ww[1] = x[1]; c.ww[2] = x[2]; c.ar0 = dist; c.kind = geom | (b.lower ? JBQ_TAG_LOWER : 0);
+    return;
+  }
+  jbq_build<T>(g, c, fr, b, geom, x, dist, rep, lane, i);
 }
 
 #define JBQ_EMIT(geom, x, dist) jbq_emit<T>(g, cs, fr, b, (geom), (x), (dist), rep, lane)
@@ -382,25 +411,27 @@ template <typename T> JB_HD void jbq_rows(T* jar, const T* ww, T mu, T ar0) {
 }
 
 // out = J_c a in WORLD comps
-template <typename T> JB_HD void jbq_J_apply(T* out, const QCon<T>& c, const QVec<T>& a) {
-  const T qa = c.kind == QK_ROTOR ? a.mo : a.la;
+template <typename T> JB_HD void jbq_J_apply(T* out, const QCon<T>& c, const QVec<T>& a, T laf, T lbf) {
+  const T qa = c.kind == QK_ROTOR ? a.mo : ((JBQ_SPREAD && c.kind == QK_LEG_F) ? laf : a.la);
+  const T qb = (JBQ_SPREAD && c.kind == QK_LEG_F) ? lbf : a.lb;
   const T* const rows[3] = {c.Jx, c.Jy, c.Jz};
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const T* J = rows[k];
-    T s = J[6] * qa + J[7] * a.lb;
+    T s = J[6] * qa + J[7] * qb;
 #pragma unroll
     for (int i = 0; i < 6; i++) s += J[i] * a.r[i];
     out[k] = s;
   }
 }
 
-// ww = J_c a - uref (dst = 0) or jv = J_c a (dst = 1) for every contact of this lane
-template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a, int dst) {
+// ww = J_c a - uref (dst = 0) or jv = J_c a (dst = 1) for every contact of this lane; (laf, lbf): the leg entries of `a`
+// in the lane that owns this lane's foreign contacts
+template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a, int dst, T laf, T lbf) {
   for (int i = 0; i < cs.n; i++) {
     QCon<T>& c = cs.c[i];
     T u[3];
-    jbq_J_apply(u, c, a);
+    jbq_J_apply(u, c, a, laf, lbf);
     if (dst == 0) { c.ww[0] = u[0] - c.uref[0]; c.ww[1] = u[1] - c.uref[1]; c.ww[2] = u[2] - c.uref[2]; }
     else { c.jv[0] = u[0]; c.jv[1] = u[1]; c.jv[2] = u[2]; }
   }
@@ -409,11 +440,11 @@ template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a,
 // This lane's constraint forces at the current ww: partial generalized force (root 6 + motor partial in out7[6], leg in
 // *fla / *flb) and the active-row mask (4 bits per contact).
 template <typename T>
-JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb) {
+JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, T* ffa, T* ffb) {
   uint32_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 7; i++) out7[i] = 0;
-  *fla = 0; *flb = 0;
+  *fla = 0; *flb = 0; *ffa = 0; *ffb = 0;
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
     T jar[4];
@@ -426,6 +457,7 @@ JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb) {
     for (int p = 0; p < 6; p++) out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
     const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
     if (c.kind == QK_ROTOR) out7[6] += gA;
+    else if ((JBQ_SPREAD && c.kind == QK_LEG_F)) { *ffa += gA; *ffb += gB; }
     else { *fla += gA; *flb += gB; }
   }
   return mask;
@@ -435,7 +467,12 @@ JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb) {
 // H: the leg block, and this lane's SHARE of the replicated block (see qarrow_factor).  W = sum over active rows of
 // D e e' has 5 distinct entries for the pyramid {z +- mu y, z -+ mu x}.
 template <typename T>
-JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H) {
+JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H, T* F15) {
+  // F15: leg-block terms of this lane's FOREIGN contacts (ca[6], aa, cb[6], ab, bb of the owning lane)
+  if (JBQ_SPREAD) {
+#pragma unroll
+    for (int q = 0; q < 15; q++) F15[q] = 0;
+  }
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
     const uint32_t m4 = mask >> (4 * i);
@@ -464,6 +501,11 @@ JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H) 
 #pragma unroll
       for (int q = 0; q < 6; q++) H.cm[q] += hA[q];
       H.mm += hA[6];
+    } else if ((JBQ_SPREAD && c.kind == QK_LEG_F)) {
+#pragma unroll
+      for (int q = 0; q < 7; q++) F15[q] += hA[q];
+#pragma unroll
+      for (int q = 0; q < 8; q++) F15[7 + q] += hB[q];
     } else {
 #pragma unroll
       for (int q = 0; q < 6; q++) { H.ca[q] += hA[q]; H.cb[q] += hB[q]; }
@@ -521,6 +563,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 
   QConSet<T> cs;
   cs.n = 0; cs.overflow = 0;
+  int hv = 0;            // the lane of this quad whose contacts were spread over the others (jbq_spread step below)
+  bool wf = false;       // warp-uniform: some quad of the warp carries foreign contacts
 
   // first moment / inertia about the origin and bias wrench: per-lane partials (this leg), summed over the quad below
   T ht[3] = {0, 0, 0}, It[6] = {0, 0, 0, 0, 0, 0};
@@ -626,8 +670,9 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     fpass.lb = -LL(L_K2) * s.qb - LL(L_D2) * s.vb;
     // collision: this leg's geoms.  Cheap height test on the sphere centres / cylinder bounding spheres first.
     {
-      QBody<T> bu = {QK_LEG, a1, p1, s.va, a2, p2, (T)0, false, LL(L_INVWU)};
-      QBody<T> bl = {QK_LEG, a1, p1, s.va, a2, p2, s.vb, true, LL(L_INVWL)};
+      // the leg's contacts are parked raw (defer) and built after jbq_spread has balanced them over the quad
+      QBody<T> bu = {QK_LEG, a1, p1, s.va, a2, p2, (T)0, false, LL(L_INVWU), JBQ_SPREAD != 0};
+      QBody<T> bl = {QK_LEG, a1, p1, s.va, a2, p2, s.vb, true, LL(L_INVWL), JBQ_SPREAD != 0};
       T c[3], gh[3], gv[3], ax[3], xa[3];
       // foot sphere (lower body)
       gh[0] = LL(L_FT_C); gh[1] = LL(L_FT_C + 1); gh[2] = LL(L_FT_C + 2);
@@ -657,6 +702,85 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           gv[0] = LL(L_UC_AX); gv[1] = LL(L_UC_AX + 1); gv[2] = LL(L_UC_AX + 2); mulMV(ax, R1, gv);
           gv[0] = LL(L_UC_XA); gv[1] = LL(L_UC_XA + 1); gv[2] = LL(L_UC_XA + 2); mulMV(xa, R1, gv);
           jbq_col_cylinder<T>(g, cs, fr, bu, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+        }
+      }
+    }
+    // ---------------- spread a heavy lane's contacts over the quad.  The per-contact loops of the solver run as many
+    // trips as the fullest lane of the WARP has contacts, and a leg that stands on the rim of its lower cylinder brings
+    // four (foot + three cap points) where the other lanes have one: the warp -- and through the phase barriers the
+    // CTA -- then waits for that lane.  The fullest lane of the quad (hv) hands its last raw contacts to the emptiest
+    // lanes until the counts differ by at most one; a helper builds them with hv's leg frame (QK_LEG_F) and the solver
+    // routes their leg-dof terms back to hv (foreign accumulators + quad sums in jbq_substep).
+    if (JBQ_SPREAD) {
+      const int n0 = cs.n;
+      const int c0 = cm.iget(n0, 0), c1 = cm.iget(n0, 1), c2 = cm.iget(n0, 2), c3 = cm.iget(n0, 3);
+      int pk = c0 | (c1 << 4) | (c2 << 8) | (c3 << 12), give = 0, M = 0, hmax = c0;
+      hv = 0;
+      if (c1 > hmax) { hv = 1; hmax = c1; }
+      if (c2 > hmax) { hv = 2; hmax = c2; }
+      if (c3 > hmax) { hv = 3; hmax = c3; }
+      if (hmax >= 3) {
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+          int m = -1, cmin = 99;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int cj = (pk >> (4 * j)) & 15;
+            if (j != hv && cj < cmin) { m = j; cmin = cj; }
+          }
+          const int ch = (pk >> (4 * hv)) & 15;
+          if (ch - cmin >= 2) { pk += (1 << (4 * m)) - (1 << (4 * hv)); give += 1 << (4 * m); M++; }
+        }
+      }
+#ifdef JBQ_DEBUG_COUNT
+      if (lane == 0) g_jbq_spread_moves += M;
+#endif
+      wf = cm.warp_any(M > 0);
+      if (wf) {
+        // move k (k = 0..M-1) takes hv's slot n_hv - M + k to the lanes in index order: give_0 moves to lane 0, ...
+        for (int k = 0; cm.warp_any(k < M); k++) {
+          T v[5] = {0, 0, 0, 0, 0};
+          if (lane == hv && k < M) {
+            const QCon<T>& c = cs.c[n0 - M + k];
+            v[0] = c.ww[0]; v[1] = c.ww[1]; v[2] = c.ww[2]; v[3] = c.ar0; v[4] = (T)c.kind;
+          }
+#pragma unroll
+          for (int i = 0; i < 5; i++) v[i] = cm.get(v[i], hv);
+          int dst = 0, acc = give & 15;
+          if (k >= acc) { dst = 1; acc += (give >> 4) & 15; }
+          if (k >= acc) { dst = 2; acc += (give >> 8) & 15; }
+          if (k >= acc) dst = 3;
+          if (k < M && lane == dst) {
+            QCon<T>& c = cs.c[cs.n];
+            cs.n++;
+            c.ww[0] = v[0]; c.ww[1] = v[1]; c.ww[2] = v[2]; c.ar0 = v[3]; c.kind = (int)v[4] | JBQ_TAG_FOREIGN;
+          }
+        }
+        if (lane == hv) cs.n = n0 - M;
+      }
+      // build: own contacts with this leg's frame, foreign ones with hv's (hinge 1 is a model constant of leg hv,
+      // hinge 2 and the joint velocities come over the quad)
+      T fa2[3] = {a2[0], a2[1], a2[2]}, fp2[3] = {p2[0], p2[1], p2[2]}, fva = s.va, fvb = s.vb;
+      if (wf) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) { fa2[i] = cm.get(fa2[i], hv); fp2[i] = cm.get(fp2[i], hv); }
+        fva = cm.get(fva, hv); fvb = cm.get(fvb, hv);
+      }
+      const T* Lh = P + JBP_L + hv;
+      const T fa1[3] = {Lh[4 * L_A1], Lh[4 * (L_A1 + 1)], Lh[4 * (L_A1 + 2)]};
+      const T fp1[3] = {Lh[4 * L_P1], Lh[4 * (L_P1 + 1)], Lh[4 * (L_P1 + 2)]};
+      for (int i = 0; i < cs.n; i++) {
+        QCon<T>& c = cs.c[i];
+        const int tag = c.kind;
+        const bool lower = (tag & JBQ_TAG_LOWER) != 0, foreign = (tag & JBQ_TAG_FOREIGN) != 0;
+        const T x[3] = {c.ww[0], c.ww[1], c.ww[2]};
+        const T dist = c.ar0;
+        if (foreign) {
+          QBody<T> b = {QK_LEG_F, fa1, fp1, fva, fa2, fp2, lower ? fvb : (T)0, lower, Lh[4 * (lower ? L_INVWL : L_INVWU)], false};
+          jbq_build<T>(g, c, fr, b, tag & 255, x, dist, rep, lane, i);
+        } else {
+          QBody<T> b = {QK_LEG, a1, p1, s.va, a2, p2, lower ? s.vb : (T)0, lower, LL(lower ? L_INVWL : L_INVWU), false};
+          jbq_build<T>(g, c, fr, b, tag & 255, x, dist, rep, lane, i);
         }
       }
     }
@@ -803,7 +927,9 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     }
     QVec<T> Ma, grad;
     qarrow_mul(cm, Ma, Mx, a);
-    jbq_apply_all(cs, a, 0);
+    T laf = 0, lbf = 0;                       // leg entries of the lane that owns this lane's foreign contacts
+    if (JBQ_SPREAD && wf) { laf = cm.get(a.la, hv); lbf = cm.get(a.lb, hv); }
+    jbq_apply_all(cs, a, 0, laf, lbf);
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
     const int maxit = JbEps<T>::newton_iters();
     bool done = !has_con, full_prev = false, exact = false;
@@ -815,8 +941,12 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     // another pass (`exact`).
     for (int trip = 0;; trip++) {
       if (trip > 0 && !cm.loop_any(!done)) break;
-      T f8[8], fla, flb;
-      const uint32_t mask = jbq_forces(cs, mu, f8, &fla, &flb);
+      T f8[8], fla, flb, ffa, ffb;
+      const uint32_t mask = jbq_forces(cs, mu, f8, &fla, &flb, &ffa, &ffb);
+      if (JBQ_SPREAD && wf) {                 // leg-dof forces of foreign contacts go home to lane hv
+        cm.sum2(ffa, ffb);
+        if (lane == hv) { fla += ffa; flb += ffb; }
+      }
       T f9[9];
 #pragma unroll
       for (int i = 0; i < 7; i++) f9[i] = f8[i];
@@ -845,7 +975,18 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         for (int i = 0; i < 6; i++) H.cm[i] = 0;
         H.mm = 0;
       }
-      jbq_hessian(cs, mu, mask, H);
+      {
+        T F15[15];
+        jbq_hessian(cs, mu, mask, H, F15);
+        if (JBQ_SPREAD && wf) {               // and so do their leg-block Hessian terms
+          cm.sumN(F15, 15);
+          if (lane == hv) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) { H.ca[q] += F15[q]; H.cb[q] += F15[7 + q]; }
+            H.aa += F15[6]; H.ab += F15[13]; H.bb += F15[14];
+          }
+        }
+      }
       cm.phase_sync(8);
       qarrow_factor<T, Comm>(cm, H, true);
       cm.phase_sync(9);
@@ -856,7 +997,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       search.la = -search.la; search.lb = -search.lb; search.mo = -search.mo;
       QVec<T> Mv;
       qarrow_mul(cm, Mv, Mx, search);
-      jbq_apply_all(cs, search, 1);
+      if (JBQ_SPREAD && wf) { laf = cm.get(search.la, hv); lbf = cm.get(search.lb, hv); }
+      jbq_apply_all(cs, search, 1, laf, lbf);
       cm.phase_sync(10);
       QVec<T> res = Ma; qv_axpy(res, (T)-1, fs);
       // g1 = s.(Ma - fs), g2 = s.Mv, d0 = s.grad (= phi'(0)); at alpha = 1: contact part of phi' and phi''

@@ -3,8 +3,6 @@
 // envs; the packed model sits in shared memory (one copy per CTA for the shared model, one per env for augmented
 // models).  See jb_quad.cuh for the per-quad algorithm and DESIGN.md for the roofline model.
 #include "jb_sim_common.cuh"
-#include "jb_quad.cuh"
-#include "jb_task.cuh"
 #include <stdlib.h>
 
 // This file is compiled twice (jitterbug_b200/build.py): as is for the shared-model kernel (384-thread CTAs, 168
@@ -14,14 +12,22 @@
 #ifdef JB_PER_ENV_BUILD
 #undef JB_BLOCK
 #define JB_BLOCK 256
+#ifndef JBQ_SPREAD
+#define JBQ_SPREAD 1          /* registers to spare here: see jb_quad.cuh */
+#endif
 #define JB_SIM_KERNEL jb_sim_kernel_perenv
 #define JB_LAUNCH_SIM jb_launch_sim_perenv
 #define JB_CONFIGURE jb_configure_kernels_perenv
 #else
+#ifndef JBQ_SPREAD
+#define JBQ_SPREAD 0
+#endif
 #define JB_SIM_KERNEL jb_sim_kernel
 #define JB_LAUNCH_SIM jb_launch_sim
 #define JB_CONFIGURE jb_configure_kernels
 #endif
+#include "jb_quad.cuh"
+#include "jb_task.cuh"
 
 #ifndef JB_SYNC_SUBSTEP
 #define JB_SYNC_SUBSTEP 1
@@ -68,6 +74,9 @@ struct QuadCommGPU {
     v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   }
+  // value held by lane `src` (0..3) of the caller's quad
+  __device__ __forceinline__ float get(float v, int src) { return __shfl_sync(0xffffffffu, v, (threadIdx.x & 28) | src); }
+  __device__ __forceinline__ int iget(int v, int src) { return __shfl_sync(0xffffffffu, v, (threadIdx.x & 28) | src); }
   __device__ __forceinline__ bool warp_any(bool p) { return __any_sync(0xffffffffu, p) != 0; }
   __device__ __forceinline__ bool loop_any(bool p) {
 #if JB_BLOCK_NEWTON
@@ -289,9 +298,9 @@ static int jb_pick_block(int N, int per_env) {
   // minimise waves x time-per-CTA with the measured per-CTA step times (ms per control step of one resident CTA).
   // Shared model: 128 threads 0.92, 256 threads 1.10, 384 threads 1.28 -- large batches want the 384-thread CTA (lowest
   // cost per env), small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs.
-  // Per-env models (the JB_PER_ENV_BUILD instantiation): 128 threads 0.82, 192 threads 1.12, 256 threads 1.45.
+  // Per-env models (the JB_PER_ENV_BUILD instantiation): 128 threads 0.78, 192 threads 1.05, 256 threads 1.31.
   const int cand[2][3] = {{384, 256, 128}, {256, 192, 128}};
-  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {1.45f, 1.12f, 0.82f}};
+  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {1.31f, 1.05f, 0.78f}};
   const int m = per_env ? 1 : 0;
   int threads = 128;
   float best = 1e30f;

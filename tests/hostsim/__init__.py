@@ -167,3 +167,10 @@ def augment(base, deltas):
     md = (jbmodel.JbModelD * n)()
     _alib.ha_augment(C.byref(base), d.ctypes.data_as(C.c_void_p), C.c_int(n), packed.ctypes.data_as(C.c_void_p), mf, md)
     return packed, mf, md
+
+
+def quad_debug_counts():
+    """(line-search iterations, Newton trips, contacts moved between lanes by the spread step) since the library loaded."""
+    out = (C.c_longlong * 3)()
+    qlib().hq_debug_counts(out)
+    return tuple(int(x) for x in out)

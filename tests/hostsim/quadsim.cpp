@@ -37,6 +37,16 @@ template <typename T> struct FiberComm {
     }
     phase++;
   }
+  T get(T v, int src) {                               // value held by lane `src` of the quad
+    Sched& S = *g_s;
+    int ph = phase & 1;
+    S.slot[ph][lane][0] = (double)v;
+    swapcontext(&S.fib[lane], &S.main_ctx);
+    T out = (T)S.slot[ph][src][0];
+    phase++;
+    return out;
+  }
+  int iget(int v, int src) { return (int)get((T)v, src); }
   T sum(T v) { exchange(&v, 1); return v; }
   void sum2(T& a, T& b) { T v[2] = {a, b}; exchange(v, 2); a = v[0]; b = v[1]; }
   void sumN(T* v, int n) { exchange(v, n); }
@@ -161,7 +171,7 @@ int hq_obs_reward(const float* P, const float* qpos, const float* qvel, int task
   return jb_obs_reward<float>(P, s, task, tg, obs, rew);
 }
 float hq_heuristic(int task, const float* obs) { return jb_heuristic<float>(task, obs); }
-void hq_debug_counts(long long* out) { out[0] = g_jbq_ls_iters; out[1] = g_jbq_newton_trips; }
+void hq_debug_counts(long long* out) { out[0] = g_jbq_ls_iters; out[1] = g_jbq_newton_trips; out[2] = g_jbq_spread_moves; }
 int hq_packed_size(void) { return JBP_SIZE; }
 void hq_pack_f64(const JbModelD* m, double* out) { jb_pack_model<double, JbModelD>(*m, out); }
 void hq_pack_f32(const JbModel* m, float* out) { jb_pack_model<float, JbModel>(*m, out); }

@@ -37,6 +37,7 @@ def test_rollout_substeps_fp64(compiled_model, packed):
     sim.qpos[3:7] = [np.cos(1.0), 0.02 * np.sin(1.0), 0.01 * np.sin(1.0), np.sin(1.0)]
     sim.forward()
     n = 0
+    moved0 = hostsim.quad_debug_counts()[2]
     for cs in range(30):
         ctrl = rng.uniform(-1, 1)
         sim.d.ctrl[0] = ctrl
@@ -52,6 +53,9 @@ def test_rollout_substeps_fp64(compiled_model, packed):
             np.testing.assert_allclose(v1, sim.qvel, atol=5e-9)
             n += 1
     assert n > 1400
+    # the rollout includes legs standing on the rim of their lower cylinder (4 contacts in one lane): the spread step
+    # that hands such contacts to the quad's other lanes has been exercised
+    assert hostsim.quad_debug_counts()[2] - moved0 > 20
 
 
 def test_forward_only_is_a_zero_length_step(compiled_model, packed):
