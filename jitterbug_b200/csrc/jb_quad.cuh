@@ -713,8 +713,10 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     // routes their leg-dof terms back to hv (foreign accumulators + quad sums in jbq_substep).
     if (JBQ_SPREAD) {
       const int n0 = cs.n;
+      int give = 0, M = 0;
+      if (cm.warp_any(n0 >= 3)) {            // the usual sub-step (at most two contacts per lane) skips the planning
       const int c0 = cm.iget(n0, 0), c1 = cm.iget(n0, 1), c2 = cm.iget(n0, 2), c3 = cm.iget(n0, 3);
-      int pk = c0 | (c1 << 4) | (c2 << 8) | (c3 << 12), give = 0, M = 0, hmax = c0;
+      int pk = c0 | (c1 << 4) | (c2 << 8) | (c3 << 12), hmax = c0;
       hv = 0;
       if (c1 > hmax) { hv = 1; hmax = c1; }
       if (c2 > hmax) { hv = 2; hmax = c2; }
@@ -731,6 +733,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           const int ch = (pk >> (4 * hv)) & 15;
           if (ch - cmin >= 2) { pk += (1 << (4 * m)) - (1 << (4 * hv)); give += 1 << (4 * m); M++; }
         }
+      }
       }
 #ifdef JBQ_DEBUG_COUNT
       if (lane == 0) g_jbq_spread_moves += M;
