@@ -1,6 +1,6 @@
 // The fused kernel (sm_100a): one QUAD of lanes per environment runs a whole control step -- n_sub_steps physics
-// sub-steps + reward + observation + episode bookkeeping -- without touching HBM in between.  CTA = 128 threads = 32
-// envs; the packed model sits in shared memory (one copy per CTA for the shared model, one per env for augmented
+// sub-steps + reward + observation + episode bookkeeping -- without touching HBM in between.  CTA = up to 384 threads =
+// 96 envs (the launcher picks the size); the packed model sits in shared memory (one copy per CTA for the shared model, one per env for augmented
 // models).  See jb_quad.cuh for the per-quad algorithm and DESIGN.md for the roofline model.
 #include "jb_sim_common.cuh"
 #include <stdlib.h>
@@ -8,7 +8,8 @@
 // This file is compiled twice (jitterbug_b200/build.py): as is for the shared-model kernel (384-thread CTAs, 168
 // registers), and with -DJB_PER_ENV_BUILD for the per-env-model kernel: there every env's 1.8 KB model is staged in shared
 // memory, which comes out of the L1 that caches the local-memory contact slots and spills, so that build trades CTA
-// size for registers (256-thread bound: ~214 registers, no spills) and runs 192-thread CTAs.
+// size for registers (256-thread bound: ~229 registers, no spills), runs 256-thread CTAs and spreads a heavy lane's
+// contacts over its quad (JBQ_SPREAD, see jb_quad.cuh).
 #ifdef JB_PER_ENV_BUILD
 #undef JB_BLOCK
 #define JB_BLOCK 256
