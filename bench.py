@@ -244,7 +244,8 @@ def run_cuda(args):
     value = world * E * args.steps / (total_ms_max * 1e-3)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H obs/reward/step_type each step)
-    h_acts = [a.cpu().numpy() for a in acts]
+    h_pin = [a.cpu().pin_memory() for a in acts]            # inputs in pinned host memory (kept alive by h_pin)
+    h_acts = [t.numpy() for t in h_pin]
     e2e_steps = max(2, min(args.steps, 8))
     env.step_host(h_acts[0])
     barrier()

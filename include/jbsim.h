@@ -64,7 +64,8 @@ int jb_sim_step(JbSim* sim, const float* actions_dev, float* obs_dev, float* rew
                 void* stream);
 
 /* Same through host buffers (the reference's numpy in / numpy out call shape): H2D of actions, step, D2H of
- * obs/reward/step_type through pinned staging, then stream synchronise. */
+ * obs/reward/step_type, then stream synchronise.  Page-locked caller buffers (cudaHostAlloc / cudaHostRegister) are the
+ * DMA end points themselves; pageable ones go through the simulator's pinned staging. */
 int jb_sim_step_host(JbSim* sim, const float* actions_host, float* obs_host, float* reward_host,
                      int32_t* step_type_host, void* stream);
 

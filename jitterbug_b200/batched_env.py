@@ -190,14 +190,19 @@ class BatchedJitterbugEnv:
         return self._obs, self._reward, self._step_type
 
     def step_host(self, actions: np.ndarray):
-        """Host-buffer entry point: numpy actions in, numpy (obs, reward, step_type) out (copies included)."""
+        """Host-buffer entry point: numpy actions in, numpy (obs, reward, step_type) out (copies included).  The returned
+        arrays are reused by the next call; pass actions in page-locked memory (e.g. ``torch.empty(N, pin_memory=True)
+        .numpy()``) to skip the library's staging copy of the inputs as well."""
         a = np.ascontiguousarray(np.asarray(actions, dtype=np.float32).reshape(-1))
         if a.shape[0] != self.num_envs:
             raise ValueError(f"expected {self.num_envs} actions")
         if not hasattr(self, "_h_obs"):
-            self._h_obs = np.empty((self.num_envs, self.obs_dim), dtype=np.float32)
-            self._h_rew = np.empty(self.num_envs, dtype=np.float32)
-            self._h_st = np.empty(self.num_envs, dtype=np.int32)
+            # page-locked result buffers: the library DMAs straight into them (pageable caller memory would go through
+            # its staging copy); the numpy arrays returned are views of these tensors and are overwritten by the next call
+            self._pin = [torch.empty((self.num_envs, self.obs_dim), dtype=torch.float32, pin_memory=True),
+                         torch.empty(self.num_envs, dtype=torch.float32, pin_memory=True),
+                         torch.empty(self.num_envs, dtype=torch.int32, pin_memory=True)]
+            self._h_obs, self._h_rew, self._h_st = (t.numpy() for t in self._pin)
         _native.check(self._lib.jb_sim_step_host(self._h, a.ctypes.data_as(C.c_void_p),
                                                  self._h_obs.ctypes.data_as(C.c_void_p),
                                                  self._h_rew.ctypes.data_as(C.c_void_p),

@@ -292,20 +292,32 @@ int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* rewar
   return 0;
 }
 
+// page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) host memory can be the DMA end point itself
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost;
+}
+
 int jb_sim_step_host(JbSim* s, const float* actions_host, float* obs_host, float* reward_host, int32_t* step_type_host, void* stream) {
   if (!s || !actions_host) return fail("jb_sim_step_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const size_t N = s->d.N, os = s->cfg.obs_stride;
-  memcpy(s->h_act, actions_host, N * sizeof(float));
-  CUDA_TRY(cudaMemcpyAsync(s->s_act, s->h_act, N * sizeof(float), cudaMemcpyHostToDevice, st));
+  // pageable caller buffers go through the simulator's pinned staging; pinned ones are copied to / from directly
+  const float* a_src = actions_host;
+  if (!is_pinned(actions_host)) { memcpy(s->h_act, actions_host, N * sizeof(float)); a_src = s->h_act; }
+  float* o_dst = obs_host && is_pinned(obs_host) ? obs_host : s->h_obs;
+  float* r_dst = reward_host && is_pinned(reward_host) ? reward_host : s->h_rew;
+  int32_t* t_dst = step_type_host && is_pinned(step_type_host) ? step_type_host : s->h_st;
+  CUDA_TRY(cudaMemcpyAsync(s->s_act, a_src, N * sizeof(float), cudaMemcpyHostToDevice, st));
   if (jb_sim_step(s, s->s_act, s->s_obs, s->s_rew, s->s_st, stream)) return 1;
-  if (obs_host) CUDA_TRY(cudaMemcpyAsync(s->h_obs, s->s_obs, N * os * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (reward_host) CUDA_TRY(cudaMemcpyAsync(s->h_rew, s->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (step_type_host) CUDA_TRY(cudaMemcpyAsync(s->h_st, s->s_st, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (obs_host) CUDA_TRY(cudaMemcpyAsync(o_dst, s->s_obs, N * os * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_host) CUDA_TRY(cudaMemcpyAsync(r_dst, s->s_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (step_type_host) CUDA_TRY(cudaMemcpyAsync(t_dst, s->s_st, N * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  if (obs_host) memcpy(obs_host, s->h_obs, N * os * sizeof(float));
-  if (reward_host) memcpy(reward_host, s->h_rew, N * sizeof(float));
-  if (step_type_host) memcpy(step_type_host, s->h_st, N * sizeof(int32_t));
+  if (obs_host && o_dst != obs_host) memcpy(obs_host, s->h_obs, N * os * sizeof(float));
+  if (reward_host && r_dst != reward_host) memcpy(reward_host, s->h_rew, N * sizeof(float));
+  if (step_type_host && t_dst != step_type_host) memcpy(step_type_host, s->h_st, N * sizeof(int32_t));
   return 0;
 }
 

@@ -239,3 +239,27 @@ def test_trajectory_recorder_mjdata_layout(tmp_path):
         p = str(tmp_path / f"traj.{ext}")
         recorder.save(p, traj)
         assert (tmp_path / f"traj.{ext}").stat().st_size > 1000
+
+
+def test_step_host_equals_device_step_with_pageable_and_pinned_buffers():
+    """The host-buffer entry point (numpy in / numpy out, copies included) returns what the device-tensor entry point
+    returns, whether the caller's action buffer is pageable (staged by the library) or page-locked (DMA end point)."""
+    import numpy as np
+    from jitterbug_b200 import BatchedJitterbugEnv
+    n = 3000
+    dev_env = BatchedJitterbugEnv("move_to_position", num_envs=n, seed=9)
+    host_env = BatchedJitterbugEnv("move_to_position", num_envs=n, seed=9)
+    pin_env = BatchedJitterbugEnv("move_to_position", num_envs=n, seed=9)
+    for e in (dev_env, host_env, pin_env):
+        e.reset()
+    rng = np.random.default_rng(0)
+    pinned = torch.empty(n, dtype=torch.float32, pin_memory=True)
+    for _ in range(4):
+        a = rng.uniform(-1, 1, n).astype(np.float32)
+        od, rd, sd = dev_env.step(torch.from_numpy(a).cuda())
+        oh, rh, sh = host_env.step_host(a)
+        pinned.copy_(torch.from_numpy(a))
+        op, rp, sp = pin_env.step_host(pinned.numpy())
+        for o, r, s in ((oh, rh, sh), (op, rp, sp)):
+            assert np.array_equal(o, od.cpu().numpy()) and np.array_equal(r, rd.cpu().numpy())
+            assert np.array_equal(s, sd.cpu().numpy())
