@@ -204,12 +204,22 @@ def run_cuda(args):
             torch.cuda.synchronize(dev)
             compile_s = time.perf_counter() - t_c
             del deltas
-    env = BatchedJitterbugEnv(TASK, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
+    task = TASK
+    if args.workload == "mixed":
+        # BASELINE.json config 3: all five tasks in one batch (task = global env id mod 5, observations padded to 19),
+        # actions from the device port of the reference's heuristic policies (one extra kernel launch per step)
+        from jitterbug_b200.batched_env import TASKS
+        task = [TASKS[(rank * E + e) % 5] for e in range(E)]
+    env = BatchedJitterbugEnv(task, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     n_act = 4
     acts = [torch.rand(E, device=dev, generator=g) * 2 - 1 for _ in range(n_act)]
     env.reset()
     stream = torch.cuda.current_stream(dev)
+    mixed = args.workload == "mixed"
+
+    def action(i):
+        return env.heuristic_actions() if mixed else acts[i % n_act]
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -220,9 +230,9 @@ def run_cuda(args):
     # untimed burn-in to the stationary regime (motor spun up, contacts active: BASELINE.md section 4 asks for
     # ~200 control steps before sampling), then the W warm-up steps of the contract
     for i in range(args.burn_in):
-        env.step(acts[i % n_act])
+        env.step(action(i))
     for i in range(args.warmup):
-        env.step(acts[i % n_act])
+        env.step(action(i))
     barrier()
     c0 = env.counters()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -230,7 +240,7 @@ def run_cuda(args):
     barrier()
     ev[0].record(stream)
     for i in range(args.steps):
-        env.step(acts[i % n_act])
+        env.step(action(i))
         ev[i + 1].record(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
@@ -290,13 +300,14 @@ def run_cuda(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{TASK}, uniform random actions, {E} envs per GPU x {world} GPU, 50 sub-steps + "
+            "config": {"workload": ("all five tasks (env id mod 5), device heuristic policies" if mixed else
+                                    f"{TASK}, uniform random actions") + f", {E} envs per GPU x {world} GPU, 50 sub-steps + "
                                    f"reward + obs per step, episodes of 1000 steps with in-kernel auto-reset"
                                    + ((f", per-env augmented models (population {args.models}, host-compiled)"
                                        if args.models > 0 else
                                        f", one augmented model per env compiled on the device ({compile_s:.2f} s)")
                                       if args.workload == "augmented" else ""),
-                       "envs_per_gpu": E, "task": TASK, "l2_policy": "inputs larger than L2 "
+                       "envs_per_gpu": E, "task": "mixed" if mixed else TASK, "l2_policy": "inputs larger than L2 "
                        f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per step vs 126 MB L2)"
                        if BYTES_PER_ENV_STEP * E > 126e6 else "inputs smaller than L2 (compute-bound kernel)",
                        "parallelism": f"env-sharded x{world}, no collective in the step path",
@@ -305,7 +316,7 @@ def run_cuda(args):
                        "mean_reward": mean_reward},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E,
                     "d2h_bytes_per_step": 4 * E * (env.obs_dim + 2), "steps": e2e_steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * (2 if mixed else 1),
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak,
                          "traffic": (_traffic_per_env() * E if _traffic_per_env() else None), "peak_source": which,
@@ -340,8 +351,9 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=1 << 20, help="envs per GPU")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--workload", default="shared", choices=["shared", "augmented"],
-                    help="shared: one model (headline); augmented: per-env randomised models (config 4)")
+    ap.add_argument("--workload", default="shared", choices=["shared", "augmented", "mixed"],
+                    help="shared: one model (headline); augmented: per-env randomised models (config 4); "
+                         "mixed: five tasks in one batch driven by the device heuristic policies (config 3)")
     ap.add_argument("--models", type=int, default=0,
                     help="augmented: 0 = one device-compiled model per env; K > 0 = host-compiled population of K")
     ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")

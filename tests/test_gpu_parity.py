@@ -34,14 +34,15 @@ def _free_run(env, steps, seed):
     return g
 
 
-def test_single_substep_state_parity(compiled_model):
+@pytest.mark.parametrize("N,warm", [(512, 120), (4096, 200)])
+def test_single_substep_state_parity(compiled_model, N, warm):
     """One physics sub-step from identical (qpos, qvel, warmstart, ctrl): qpos within 1e-6, qvel within 1e-5 relative
-    (fp32 kernel vs fp64 oracle; the north_star tolerance is 1e-5), active contact sets identical."""
+    (fp32 kernel vs fp64 oracle; the north_star tolerance is 1e-5), active contact sets identical.  (4096, 200) is
+    BASELINE.json's config 2: 4096 move_from_origin envs, 200 warm-up steps so that contacts are active."""
     _need_gpu()
     O = _oracle()
-    N = 512
     env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=1)
-    g = _free_run(env, 120, 7)
+    g = _free_run(env, warm, 7)
     qpos, qvel, warm = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
     # same model, one sub-step per control step
     env1 = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=1, control_timestep=0.0002, time_limit=float("inf"))
