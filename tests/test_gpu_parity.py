@@ -296,3 +296,55 @@ def test_long_horizon_return_distributions(compiled_model):
             rc[e] += tk.get_reward()
     ksh = stats.ks_2samp(rg, rc)
     assert ksh.pvalue > 0.01, (ksh, rg.mean(), rc.mean())
+
+
+def test_per_env_kernel_single_substep_parity_including_spread_contacts(compiled_model):
+    """The per-env-model instantiation of the step kernel (which spreads a heavy lane's contacts over its quad) against
+    the oracle, one sub-step from identical contact-rich states; every env carries the stock model, so the states and
+    the oracle are the shared-model ones.  The states with a leg standing on its lower-cylinder cap (>= 4 contacts on
+    one leg, the case the spread step exists for) must be present and must agree like the others."""
+    _need_gpu()
+    O = _oracle()
+    N = 2048
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=1)
+    g = _free_run(env, 200, 7)
+    qpos, qvel, warm = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+    # N copies of the packed stock model (test-side pack helper: the same jb_pack_model the library uses)
+    from jitterbug_b200.model import fill_struct, flatten_model
+    import hostsim
+    stock = hostsim.pack(fill_struct(flatten_model(compiled_model)), double=False)
+    pk = torch.from_numpy(np.tile(stock, (N, 1))).to(env.device).contiguous()
+    env1 = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=1, control_timestep=0.0002, time_limit=float("inf"),
+                               packed_models=pk)
+    env1.reset()
+    env1.set_state(qpos, qvel, warm, step_count=np.ones(N))
+    a = (torch.rand(N, device=env.device, generator=g) * 2 - 1)
+    ncon, geom, dist = [t.cpu().numpy() for t in env1.contacts(32)]
+    env1.step(a)
+    q1, v1, _ = [t.cpu().numpy().astype(np.float64) for t in env1.get_state()]
+    a = a.cpu().numpy()
+    sim = O.OracleSim(compiled_model)
+    worst_q = worst_v = 0.0
+    heavy = checked = 0
+    leg_of = {g_: (g_ - 5) // 4 for g_ in range(5, 21)}
+    for e in range(N):
+        sim.set_state(qpos[e], qvel[e], warm[e], ctrl=a[e])
+        sim.step1()
+        g2, d2, ex, _ = sim.contacts()
+        if any(abs(dd) < 1e-6 for dd in d2):
+            continue
+        act = [int(gg) for gg, xx in zip(g2, ex) if not xx]
+        assert [int(geom[e, i]) for i in range(ncon[e])] == act
+        per_leg = np.bincount([leg_of[gg] for gg in act if gg in leg_of], minlength=4)
+        is_heavy = per_leg.max() >= 4
+        sim.step2()
+        dq = (np.abs(q1[e] - sim.qpos) / np.maximum(np.abs(sim.qpos), 1.0)).max()
+        scale = np.concatenate([np.full(3, max(1e-2, np.abs(sim.qvel[0:3]).max())), np.full(3, max(1.0, np.abs(sim.qvel[3:6]).max())),
+                                np.full(8, max(1.0, np.abs(sim.qvel[6:14]).max())), np.full(1, max(1.0, abs(sim.qvel[14])))])
+        dv = (np.abs(v1[e] - sim.qvel) / scale).max()
+        worst_q, worst_v = max(worst_q, dq), max(worst_v, dv)
+        heavy += int(is_heavy)
+        checked += 1
+    print(f"per-env kernel: {checked} envs checked, {heavy} with a 4-contact leg, worst qpos {worst_q:.2e}, qvel {worst_v:.2e}")
+    assert checked > N * 0.9 and heavy >= 10
+    assert worst_q < 1e-6 and worst_v < 1e-5
