@@ -38,7 +38,7 @@ typedef struct {
 } JbSimConfig;
 
 /* Replaces Physics.from_xml_string + control.Environment construction (jitterbug.py:81-90).
- * `models`: n_models == 1 (shared model, kept in constant memory) or n_models == num_envs (per-env augmented models,
+ * `models`: n_models == 1 (shared model, staged in shared memory once per CTA) or n_models == num_envs (per-env augmented models,
  * augmented_jitterbug.py:95-267).  `task_ids_host`: num_envs task ids (JB_TASK_*), or NULL for all move_from_origin. */
 int jb_sim_create(JbSim** out, const JbSimConfig* cfg, const JbModel* models_host, int n_models,
                   const int32_t* task_ids_host);
@@ -69,6 +69,11 @@ int jb_sim_step(JbSim* sim, const float* actions_dev, float* obs_dev, float* rew
 int jb_sim_step_host(JbSim* sim, const float* actions_host, float* obs_host, float* reward_host,
                      int32_t* step_type_host, void* stream);
 
+/* task.get_observation(physics) and task.get_reward(physics) (jitterbug.py:673-763, :891-925) evaluated at the CURRENT
+ * state of every env, without stepping.  obs_dev[num_envs * obs_stride] and / or reward_dev[num_envs] (either may be
+ * NULL). */
+int jb_sim_observe(JbSim* sim, float* obs_dev, float* reward_dev, void* stream);
+
 /* heuristic_policies.* (heuristic_policies.py:6-136) evaluated on device from an observation buffer. */
 int jb_sim_heuristic_actions(JbSim* sim, const float* obs_dev, float* actions_dev, void* stream);
 
@@ -87,6 +92,18 @@ int jb_sim_set_step_count(JbSim* sim, const int32_t* count_dev, void* stream);
  * to `max_con` of them the MuJoCo geom id of the non-floor geom and the signed distance, in ascending geom id.
  * ncon_dev[num_envs]; geom_dev, dist_dev: [num_envs][max_con]. */
 int jb_sim_get_contacts(JbSim* sim, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream);
+
+/* Slot order of the step kernel.  The kernel hands the envs to its quads in a load-sorted order (heavy envs -- many
+ * contacts in one leg's lane, extra Newton trips -- share warps and CTAs instead of stalling light ones); the order is
+ * recomputed on the device after every jb_sim_step from that step's load records.  It is a scheduling decision only:
+ * per-env results are bit-identical for any order.  mode: JB_ORDER_AUTO (default), JB_ORDER_IDENTITY (slot i = env i),
+ * JB_ORDER_EXPLICIT (perm_dev[num_envs], a permutation of the env ids; copied). */
+enum { JB_ORDER_AUTO = 0, JB_ORDER_IDENTITY = 1, JB_ORDER_EXPLICIT = 2 };
+int jb_sim_set_slot_order(JbSim* sim, int mode, const int32_t* perm_dev, void* stream);
+int jb_sim_get_slot_order(JbSim* sim, int32_t* perm_dev, void* stream);
+/* load record of the last jb_sim_step per env, load_dev[num_envs][4]: contacts summed over the sub-steps in the fullest
+ * lane of the env's quad, sub-steps with >= 3 / >= 2 contacts in one lane, Newton trips. */
+int jb_sim_get_load(JbSim* sim, int32_t* load_dev, void* stream);
 
 /* counters since creation: [0] physics sub-steps, [1] Newton iterations, [2] active contacts summed over sub-steps,
  * [3] contact-slot overflows, [4] diverged-state resets.  Synchronises the device. */

@@ -52,6 +52,7 @@ SYMBOLS = {
     "jb_sim_reset": (C.c_int, [_P, _P, _P, _P]),
     "jb_sim_step": (C.c_int, [_P, _P, _P, _P, _P, _P]),
     "jb_sim_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P]),
+    "jb_sim_observe": (C.c_int, [_P, _P, _P, _P]),
     "jb_sim_heuristic_actions": (C.c_int, [_P, _P, _P, _P]),
     "jb_sim_get_state": (C.c_int, [_P, _P, _P, _P, _P]),
     "jb_sim_set_state": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -60,6 +61,9 @@ SYMBOLS = {
     "jb_sim_get_step_count": (C.c_int, [_P, _P, _P]),
     "jb_sim_set_step_count": (C.c_int, [_P, _P, _P]),
     "jb_sim_get_contacts": (C.c_int, [_P, _P, _P, _P, C.c_int, _P]),
+    "jb_sim_set_slot_order": (C.c_int, [_P, C.c_int, _P, _P]),
+    "jb_sim_get_slot_order": (C.c_int, [_P, _P, _P]),
+    "jb_sim_get_load": (C.c_int, [_P, _P, _P]),
     "jb_sim_get_counters": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "jb_sim_get_phase_cycles": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "jb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),

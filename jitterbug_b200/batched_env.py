@@ -209,6 +209,15 @@ class BatchedJitterbugEnv:
                                                  self._h_st.ctypes.data_as(C.c_void_p), self._stream()))
         return self._h_obs, self._h_rew, self._h_st
 
+    def observe(self):
+        """``task.get_observation`` / ``task.get_reward`` at the current state (no physics advance): fresh
+        ``(obs[N, D], reward[N])`` tensors."""
+        obs = torch.empty(self.num_envs, self.obs_dim, device=self.device, dtype=torch.float32)
+        rew = torch.empty(self.num_envs, device=self.device, dtype=torch.float32)
+        _native.check(self._lib.jb_sim_observe(self._h, C.c_void_p(obs.data_ptr()), C.c_void_p(rew.data_ptr()),
+                                               self._stream()))
+        return obs, rew
+
     def heuristic_actions(self, obs: Optional[torch.Tensor] = None) -> torch.Tensor:
         """heuristic_policies.<task>(ts) for every env, on device (heuristic_policies.py:59-118)."""
         obs = self._obs if obs is None else obs.contiguous()
@@ -263,6 +272,31 @@ class BatchedJitterbugEnv:
         _native.check(self._lib.jb_sim_get_contacts(self._h, C.c_void_p(ncon.data_ptr()), C.c_void_p(geom.data_ptr()),
                                                     C.c_void_p(dist.data_ptr()), max_con, self._stream()))
         return ncon, geom, dist
+
+    # ------------------------------------------------------------------ slot order of the step kernel (scheduling only)
+    def set_slot_order(self, mode: Union[str, torch.Tensor] = "auto"):
+        """``"auto"`` (default: load-sorted on the device after every step), ``"identity"``, or an int32 CUDA tensor
+        holding a permutation of the env ids.  Results per env do not depend on it (see include/jbsim.h)."""
+        if isinstance(mode, str):
+            code = {"auto": 0, "identity": 1}[mode]
+            _native.check(self._lib.jb_sim_set_slot_order(self._h, code, None, self._stream()))
+        else:
+            perm = mode.to(device=self.device, dtype=torch.int32).contiguous()
+            if perm.shape != (self.num_envs,):
+                raise ValueError("the slot order must have num_envs entries")
+            _native.check(self._lib.jb_sim_set_slot_order(self._h, 2, C.c_void_p(perm.data_ptr()), self._stream()))
+
+    def get_slot_order(self) -> torch.Tensor:
+        perm = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        _native.check(self._lib.jb_sim_get_slot_order(self._h, C.c_void_p(perm.data_ptr()), self._stream()))
+        return perm
+
+    def load(self) -> torch.Tensor:
+        """Load record of the last step per env, int32 [N, 4]: contacts summed over the sub-steps in the fullest lane,
+        sub-steps with >= 3 / >= 2 contacts in one lane, Newton trips."""
+        ld = torch.empty(self.num_envs, 4, dtype=torch.int32, device=self.device)
+        _native.check(self._lib.jb_sim_get_load(self._h, C.c_void_p(ld.data_ptr()), self._stream()))
+        return ld
 
     def counters(self):
         """dict of device counters since creation (synchronises)."""

@@ -1,6 +1,6 @@
 """Builds ``jitterbug_b200/_lib/libjbsim.so`` (CUDA, sm_100a) in-tree with nvcc.
 
-Five objects: the fused quad-per-env step kernel in its two instantiations (shared model / per-env models), the C-ABI +
+Six objects: the fused quad-per-env step kernel in its two instantiations (shared model / per-env models), the C-ABI +
 utility kernels, the observation encoder and the on-device model compiler; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
 """
 
@@ -18,7 +18,7 @@ LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
 # (source, object stem, extra flags): the step kernel is instantiated twice, see the head of jb_sim_kernel.cu
 UNITS = [("jb_sim_kernel.cu", "jb_sim_kernel", []), ("jb_sim_kernel.cu", "jb_sim_kernel_perenv", ["-DJB_PER_ENV_BUILD"]),
-         ("jb_api.cu", "jb_api", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
+         ("jb_api.cu", "jb_api", []), ("jb_sort.cu", "jb_sort", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
 # -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
 # 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -17,6 +17,23 @@ int jb_set_error(const std::string& msg) { return fail(msg); }   // for the othe
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_));              \
   } while (0)
 
+// A JbSim is bound to one device: every entry point makes that device current for the duration of the call and restores
+// the caller's device afterwards (two simulators on two GPUs in one process, or calls from another host thread).
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched && prev >= 0) cudaSetDevice(prev); }
+};
+#define JB_GUARD(s) DeviceGuard guard_((s)->cfg.device)
+struct DevBuf {                               // scope-owned device allocation
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  void* release() { void* q = p; p = nullptr; return q; }
+};
+
 struct JbSim {
   JbSimConfig cfg;
   JbDev d;
@@ -25,6 +42,10 @@ struct JbSim {
   // pinned staging for the host-buffer entry point
   float *h_act, *h_obs, *h_rew; int32_t* h_st;
   float *s_act, *s_obs, *s_rew; int32_t* s_st;
+  // load-sorted slot order (jb_sort.cu): perm buffers [2][N] (double-buffered), the scan scratch, and whether a STEP
+  // launch re-sorts for the next one
+  int* perm_buf; int* sort_scratch; int perm_cur; int auto_sort;
+  int seg_sub;                      // sub-steps per launch of a control step when the slot order is being sorted
 };
 
 static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
@@ -33,7 +54,10 @@ static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
   return (s->per_env || force256) ? jb_launch_sim_perenv(s->d, a, st) : jb_launch_sim(s->d, a, st);
 }
 
-#define JB_REP (4 * 8)   /* 4 lanes x JBQ_CAP staging slots per env */
+#ifndef JBQ_CAP
+#define JBQ_CAP 8
+#endif
+#define JB_REP (4 * JBQ_CAP)   /* 4 lanes x JBQ_CAP staging slots per env (same macro as jb_quad.cuh) */
 
 // staging [N][32] (-1 = empty) -> compact lists in ascending MuJoCo geom id
 __global__ void jb_compact_contacts_kernel(int N, const int* rep_geom, const float* rep_dist, int* ncon, int* geom,
@@ -101,6 +125,33 @@ __global__ void jb_target_kernel(const __grid_constant__ JbDev d, float* tgt, in
     if (set) d.target[i * d.N + e] = tgt[(size_t)e * 4 + i];
     else tgt[(size_t)e * 4 + i] = d.target[i * d.N + e];
   }
+}
+// task.get_observation(physics) / task.get_reward(physics) at the current state, one thread per env
+struct JbRootView { float pos[3], quat[4], vlin[3], w[3], qm, vm; };
+__global__ void jb_observe_kernel(const __grid_constant__ JbDev d, float* __restrict__ obs_out, float* __restrict__ reward_out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.N) return;
+  const int N = d.N;
+  JbRootView s;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { s.pos[i] = d.qpos[i * N + e]; s.vlin[i] = d.qvel[i * N + e]; s.w[i] = d.qvel[(3 + i) * N + e]; }
+#pragma unroll
+  for (int i = 0; i < 4; i++) s.quat[i] = d.qpos[(3 + i) * N + e];
+  s.qm = d.qpos[15 * N + e]; s.vm = d.qvel[14 * N + e];       // wrapped motor angle: the observation wraps it anyway
+  JbTarget<float> tg = {d.target[e], d.target[N + e], d.target[2 * N + e], d.target[3 * N + e]};
+  const float* g = d.packed + (d.per_env ? (size_t)e * JBP_SIZE : 0);
+  float obs[JB_OBS_MAX], rew;
+  const int n = jb_obs_reward<float>(g, s, d.task[e], tg, obs, &rew);
+  if (obs_out) {
+    float* o = obs_out + (size_t)e * d.obs_stride;
+    for (int i = 0; i < d.obs_stride; i++) o[i] = i < n ? obs[i] : 0.f;
+  }
+  if (reward_out) reward_out[e] = rew;
+}
+
+__global__ void jb_iota_kernel(int* p, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < N) p[e] = e;
 }
 __global__ void jb_count_kernel(const __grid_constant__ JbDev d, int* cnt, int set) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,14 +232,19 @@ static int sim_fill(JbSim* s, const JbSimConfig* cfg, const int32_t* task_ids_ho
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
   CUDA_TRY(jb_configure_kernels_perenv());
   CUDA_TRY(jb_configure_kernels());
-  CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
-  CUDA_TRY(cudaMallocHost(&s->h_obs, N * cfg->obs_stride * sizeof(float)));
-  CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));
-  CUDA_TRY(cudaMallocHost(&s->h_st, N * sizeof(int32_t)));
-  CUDA_TRY(cudaMalloc(&s->s_act, N * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&s->s_obs, N * cfg->obs_stride * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&s->s_rew, N * sizeof(float)));
-  CUDA_TRY(cudaMalloc(&s->s_st, N * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&d.load, N * sizeof(int4)));
+  CUDA_TRY(cudaMemset(d.load, 0, N * sizeof(int4)));
+  CUDA_TRY(cudaMalloc(&s->perm_buf, 2 * N * sizeof(int)));
+  CUDA_TRY(cudaMalloc(&s->sort_scratch, (size_t)jb_sort_scratch_ints((int)N) * sizeof(int)));
+  d.perm = nullptr;                      // identity until the first sort
+  s->perm_cur = 0;
+  // Sorting pays when the grid is several waves deep (the heavy envs then fill whole CTAs of their own); small batches
+  // (parity configurations, the single-env adapter) keep slot i = env i and one launch per control step.
+  s->auto_sort = N >= (size_t)JB_SORT_MIN_ENVS ? 1 : 0;
+  // An env's load is persistent over ~10 sub-steps, much less over 50 (measured: profiles/README.md, round 2): the
+  // control step is cut into launches of JB_SEGMENT_SUBSTEPS sub-steps and the order re-sorted after each.
+  s->seg_sub = JB_SEGMENT_SUBSTEPS;
+  if (const char* e = getenv("JBSIM_SEGMENT")) s->seg_sub = atoi(e) > 0 ? atoi(e) : (1 << 30);
   return 0;
 }
 
@@ -211,7 +267,7 @@ static int check_config(const JbSimConfig* cfg) {
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) return fail("jb_sim_create: no CUDA device (this library has no CPU fallback)");
-  CUDA_TRY(cudaSetDevice(cfg->device));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("jb_sim_create: no such CUDA device");
   return 0;
 }
 
@@ -226,28 +282,26 @@ int jb_sim_create_indexed(JbSim** out, const JbSimConfig* cfg, const JbModel* mo
     for (int e = 0; e < cfg->num_envs; e++)
       if (model_index_host[e] < 0 || model_index_host[e] >= n_models) return fail("jb_sim_create: model index out of range");
   if (int rc = check_config(cfg)) return rc;
+  DeviceGuard guard_(cfg->device);
   const size_t N = cfg->num_envs;
   // pack the model(s) into the lane-interleaved float layout the quad kernel stages in shared memory
   const size_t nm = (size_t)n_models;
   std::vector<float> packed(nm * JBP_SIZE);
   for (size_t i = 0; i < nm; i++) jb_pack_model<float, JbModel>(models_host[i], packed.data() + i * JBP_SIZE);
-  float* pdev = nullptr;
-  CUDA_TRY(cudaMalloc(&pdev, packed.size() * sizeof(float)));
-  CUDA_TRY(cudaMemcpy(pdev, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
+  DevBuf pdev, idev, full;                   // released on every early return; release() hands ownership on
+  CUDA_TRY(cudaMalloc(&pdev.p, packed.size() * sizeof(float)));
+  CUDA_TRY(cudaMemcpy(pdev.p, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice));
   if (model_index_host) {
     // K distinct models + per-env index: expand on the device (the host never holds num_envs models)
-    int* idev = nullptr;
-    float* full = nullptr;
-    CUDA_TRY(cudaMalloc(&idev, N * sizeof(int)));
-    CUDA_TRY(cudaMemcpy(idev, model_index_host, N * sizeof(int), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&full, N * JBP_SIZE * sizeof(float)));
-    jb_expand_models_kernel<<<(unsigned)N, 128>>>(full, pdev, idev, (int)N);
+    CUDA_TRY(cudaMalloc(&idev.p, N * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(idev.p, model_index_host, N * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&full.p, N * JBP_SIZE * sizeof(float)));
+    jb_expand_models_kernel<<<(unsigned)N, 128>>>((float*)full.p, (const float*)pdev.p, (const int*)idev.p, (int)N);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(idev); cudaFree(pdev);
-    pdev = full;
+    return sim_create_common(out, cfg, task_ids_host, (float*)full.release(), true);
   }
-  return sim_create_common(out, cfg, task_ids_host, pdev, n_models != 1 || model_index_host != nullptr);
+  return sim_create_common(out, cfg, task_ids_host, (float*)pdev.release(), n_models != 1);
 }
 
 int jb_sim_create_packed(JbSim** out, const JbSimConfig* cfg, const float* packed_dev, int n_models,
@@ -255,19 +309,21 @@ int jb_sim_create_packed(JbSim** out, const JbSimConfig* cfg, const float* packe
   if (!out || !cfg || !packed_dev) return fail("jb_sim_create_packed: null argument");
   if (n_models != 1 && n_models != cfg->num_envs) return fail("jb_sim_create_packed: n_models must be 1 or num_envs");
   if (int rc = check_config(cfg)) return rc;
-  float* pdev = nullptr;
+  DeviceGuard guard_(cfg->device);
+  DevBuf pdev;
   const size_t bytes = (size_t)n_models * JBP_SIZE * sizeof(float);
-  CUDA_TRY(cudaMalloc(&pdev, bytes));
-  CUDA_TRY(cudaMemcpy(pdev, packed_dev, bytes, cudaMemcpyDeviceToDevice));
-  return sim_create_common(out, cfg, task_ids_host, pdev, n_models != 1);
+  CUDA_TRY(cudaMalloc(&pdev.p, bytes));
+  CUDA_TRY(cudaMemcpy(pdev.p, packed_dev, bytes, cudaMemcpyDeviceToDevice));
+  return sim_create_common(out, cfg, task_ids_host, (float*)pdev.release(), n_models != 1);
 }
 
 void jb_sim_destroy(JbSim* s) {
   if (!s) return;
-  cudaSetDevice(s->cfg.device);
+  JB_GUARD(s);
   JbDev& d = s->d;
   cudaFree(d.qpos); cudaFree(d.qvel); cudaFree(d.warm); cudaFree(d.target); cudaFree(d.rev); cudaFree(d.task);
   cudaFree(d.step_count); cudaFree(d.episode); cudaFree(d.reset_next); cudaFree(d.counters);
+  cudaFree(d.load); cudaFree(s->perm_buf); cudaFree(s->sort_scratch);
   if (d.packed) cudaFree((void*)d.packed);
   if (s->rep_geom) cudaFree(s->rep_geom);
   if (s->rep_dist) cudaFree(s->rep_dist);
@@ -278,17 +334,49 @@ void jb_sim_destroy(JbSim* s) {
 
 int jb_sim_reset(JbSim* s, const uint8_t* mask_dev, float* obs_dev, void* stream) {
   if (!s) return fail("jb_sim_reset: null sim");
+  JB_GUARD(s);
   cudaStream_t st = (cudaStream_t)stream;
-  JbLaunchArgs a = {JB_MODE_RESET, mask_dev, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr};
+  JbLaunchArgs a = {JB_MODE_RESET, mask_dev, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr, 0, 1, 1};
   CUDA_TRY(launch(s, a, st));
   return 0;
 }
 
 int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* reward_dev, int32_t* step_type_dev, void* stream) {
   if (!s || !actions_dev) return fail("jb_sim_step: null argument");
+  JB_GUARD(s);
   cudaStream_t st = (cudaStream_t)stream;
-  JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr};
-  CUDA_TRY(launch(s, a, st));
+  JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr, 0, 0, 0};
+  const int n_sub = s->d.n_sub, seg = s->auto_sort ? s->seg_sub : n_sub;
+  for (int k0 = 0; k0 < n_sub; k0 += seg) {
+    a.sub_count = n_sub - k0 < seg ? n_sub - k0 : seg;
+    a.first = k0 == 0;
+    a.last = k0 + a.sub_count >= n_sub;
+    CUDA_TRY(launch(s, a, st));
+    if (s->auto_sort) {
+      // slot order of the NEXT launch from this segment's load records (jb_sort.cu); double-buffered: the kernel just
+      // enqueued still reads the current order
+      int* next = s->perm_buf + (size_t)(s->perm_cur ^ 1) * s->d.N;
+      CUDA_TRY(jb_sort_by_load(s->d.load, s->d.N, a.sub_count, next, s->sort_scratch, st));
+      s->perm_cur ^= 1;
+      s->d.perm = next;
+    }
+  }
+  return 0;
+}
+
+// staging of the host-buffer entry point, allocated on its first use (170 MB at 1 Mi envs that device-resident callers
+// never need)
+static int ensure_host_staging(JbSim* s) {
+  if (s->s_act) return 0;
+  const size_t N = s->d.N, os = s->cfg.obs_stride;
+  CUDA_TRY(cudaMallocHost(&s->h_act, N * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_obs, N * os * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_rew, N * sizeof(float)));
+  CUDA_TRY(cudaMallocHost(&s->h_st, N * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&s->s_obs, N * os * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&s->s_rew, N * sizeof(float)));
+  CUDA_TRY(cudaMalloc(&s->s_st, N * sizeof(int32_t)));
+  CUDA_TRY(cudaMalloc(&s->s_act, N * sizeof(float)));
   return 0;
 }
 
@@ -302,6 +390,8 @@ static bool is_pinned(const void* p) {
 int jb_sim_step_host(JbSim* s, const float* actions_host, float* obs_host, float* reward_host, int32_t* step_type_host, void* stream) {
   if (!s || !actions_host) return fail("jb_sim_step_host: null argument");
   cudaStream_t st = (cudaStream_t)stream;
+  JB_GUARD(s);
+  if (ensure_host_staging(s)) return 1;
   const size_t N = s->d.N, os = s->cfg.obs_stride;
   // pageable caller buffers go through the simulator's pinned staging; pinned ones are copied to / from directly
   const float* a_src = actions_host;
@@ -321,8 +411,17 @@ int jb_sim_step_host(JbSim* s, const float* actions_host, float* obs_host, float
   return 0;
 }
 
+int jb_sim_observe(JbSim* s, float* obs_dev, float* reward_dev, void* stream) {
+  if (!s || (!obs_dev && !reward_dev)) return fail("jb_sim_observe: null argument");
+  JB_GUARD(s);
+  jb_observe_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, obs_dev, reward_dev);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int jb_sim_heuristic_actions(JbSim* s, const float* obs_dev, float* actions_dev, void* stream) {
   if (!s || !obs_dev || !actions_dev) return fail("jb_sim_heuristic_actions: null argument");
+  JB_GUARD(s);
   jb_heuristic_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, obs_dev, actions_dev);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -330,48 +429,55 @@ int jb_sim_heuristic_actions(JbSim* s, const float* obs_dev, float* actions_dev,
 
 int jb_sim_get_state(JbSim* s, float* qpos_dev, float* qvel_dev, float* warm_dev, void* stream) {
   if (!s) return fail("jb_sim_get_state: null sim");
+  JB_GUARD(s);
   jb_get_state_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, qpos_dev, qvel_dev, warm_dev);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_set_state(JbSim* s, const float* qpos_dev, const float* qvel_dev, const float* warm_dev, void* stream) {
   if (!s) return fail("jb_sim_set_state: null sim");
+  JB_GUARD(s);
   jb_set_state_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, qpos_dev, qvel_dev, warm_dev);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_get_target(JbSim* s, float* target_dev, void* stream) {
   if (!s || !target_dev) return fail("jb_sim_get_target: null argument");
+  JB_GUARD(s);
   jb_target_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, target_dev, 0);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_set_target(JbSim* s, const float* target_dev, void* stream) {
   if (!s || !target_dev) return fail("jb_sim_set_target: null argument");
+  JB_GUARD(s);
   jb_target_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, (float*)target_dev, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_get_step_count(JbSim* s, int32_t* count_dev, void* stream) {
   if (!s || !count_dev) return fail("jb_sim_get_step_count: null argument");
+  JB_GUARD(s);
   jb_count_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, count_dev, 0);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_set_step_count(JbSim* s, const int32_t* count_dev, void* stream) {
   if (!s || !count_dev) return fail("jb_sim_set_step_count: null argument");
+  JB_GUARD(s);
   jb_count_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, (int*)count_dev, 1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream) {
   if (!s || !ncon_dev || !geom_dev || !dist_dev || max_con <= 0) return fail("jb_sim_get_contacts: bad argument");
+  JB_GUARD(s);
   cudaStream_t st = (cudaStream_t)stream;
   if (!s->rep_geom) {
     CUDA_TRY(cudaMalloc(&s->rep_geom, (size_t)s->d.N * JB_REP * sizeof(int)));
     CUDA_TRY(cudaMalloc(&s->rep_dist, (size_t)s->d.N * JB_REP * sizeof(float)));
   }
-  JbLaunchArgs a = {JB_MODE_CONTACTS, nullptr, nullptr, nullptr, nullptr, nullptr, s->rep_geom, s->rep_dist};
+  JbLaunchArgs a = {JB_MODE_CONTACTS, nullptr, nullptr, nullptr, nullptr, nullptr, s->rep_geom, s->rep_dist, 0, 1, 1};
   CUDA_TRY(launch(s, a, st));
   jb_compact_contacts_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, st>>>(s->d.N, s->rep_geom, s->rep_dist, ncon_dev, geom_dev,
                                                                     dist_dev, max_con);
@@ -381,13 +487,54 @@ int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* d
 // profiling builds (-DJBQ_PHASE_TIMERS): per-phase clock64 sums of lane 0 of every warp, slots 9..15
 int jb_sim_get_phase_cycles(JbSim* s, unsigned long long* out8_host) {
   if (!s || !out8_host) return fail("jb_sim_get_phase_cycles: null argument");
+  JB_GUARD(s);
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out8_host, s->d.counters + 8, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;
 }
 
+__global__ void jb_copy_load_kernel(const int4* src, int4* dst, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < N) dst[e] = src[e];
+}
+
+int jb_sim_get_load(JbSim* s, int32_t* load_dev, void* stream) {
+  if (!s || !load_dev) return fail("jb_sim_get_load: null argument");
+  JB_GUARD(s);
+  jb_copy_load_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d.load, reinterpret_cast<int4*>(load_dev), s->d.N);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int jb_sim_set_slot_order(JbSim* s, int mode, const int32_t* perm_dev, void* stream) {
+  if (!s) return fail("jb_sim_set_slot_order: null sim");
+  JB_GUARD(s);
+  if (mode == JB_ORDER_AUTO) { s->auto_sort = 1; return 0; }      // also for batches below JB_SORT_MIN_ENVS (tests)
+  s->auto_sort = 0;
+  if (mode == JB_ORDER_IDENTITY) { s->d.perm = nullptr; return 0; }
+  if (mode != JB_ORDER_EXPLICIT || !perm_dev) return fail("jb_sim_set_slot_order: bad mode / null permutation");
+  int* next = s->perm_buf + (size_t)(s->perm_cur ^ 1) * s->d.N;
+  CUDA_TRY(cudaMemcpyAsync(next, perm_dev, (size_t)s->d.N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  s->perm_cur ^= 1;
+  s->d.perm = next;
+  return 0;
+}
+
+int jb_sim_get_slot_order(JbSim* s, int32_t* perm_dev, void* stream) {
+  if (!s || !perm_dev) return fail("jb_sim_get_slot_order: null argument");
+  JB_GUARD(s);
+  if (s->d.perm) {
+    CUDA_TRY(cudaMemcpyAsync(perm_dev, s->d.perm, (size_t)s->d.N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  } else {
+    jb_iota_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(perm_dev, s->d.N);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
 int jb_sim_get_counters(JbSim* s, unsigned long long* out5_host) {
   if (!s || !out5_host) return fail("jb_sim_get_counters: null argument");
+  JB_GUARD(s);
   CUDA_TRY(cudaDeviceSynchronize());
   CUDA_TRY(cudaMemcpy(out5_host, s->d.counters, 5 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return 0;

@@ -537,7 +537,7 @@ template <typename T> JB_HD uint32_t jbq_ls_local(const QConSet<T>& cs, T mu, T 
 // P: packed model (jb_packed.h); lane in [0,4).  forward_only: stop after the constraint solve (mj_forward).
 template <typename T, typename Comm>
 JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, bool forward_only, int* iter_accum,
-                       int* ncon_accum, int* overflow_accum, const QReport<T>* rep) {
+                       int* ncon_accum, int* overflow_accum, const QReport<T>* rep, int* lane_load = nullptr) {
   // forward_only (mj_forward: everything up to qacc / qacc_warmstart) is a sub-step of length zero, so that every
   // thread of a CTA follows the same control flow whatever its env is doing (the phase barriers below rely on it)
   const T* g = P;
@@ -911,6 +911,10 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   qv_axpy(fs, (T)-1, bias);
   JBQ_TICK(4);
   const int ncon = cm.isum(cs.n);
+  // this lane's share of the env's load record: sum of contacts | sub-steps with >= 3 | sub-steps with >= 2 | latest count
+  if (lane_load)                         // bits 0-11 / 12-19 / 20-27 accumulate, bits 28-31: contacts at the latest sub-step
+    *lane_load = (int)((((unsigned)*lane_load & 0x0fffffffu) + (unsigned)(cs.n + (cs.n >= 3 ? (1 << 12) : 0) + (cs.n >= 2 ? (1 << 20) : 0))) |
+                       ((unsigned)cs.n << 28));
 
   // ---------------- constraint solve (primal Newton).  Control flow is kept WARP-uniform (Comm::warp_any): every quad
   // of the warp runs the same number of Newton / line-search iterations, quads that are finished take zero-length

@@ -26,8 +26,10 @@
 struct JbDev {
   float *qpos, *qvel, *warm, *target;
   int *rev, *task, *step_count, *episode;
-  unsigned char* reset_next;
+  unsigned char* reset_next;        // 0: stepping, 1: the next STEP resets the env, 2: reset earlier in the running control step
   unsigned long long* counters;     // 5
+  const int* perm;                  // slot -> env: quad `slot` of the grid simulates env perm[slot] (NULL = identity)
+  int4* load;                       // per env, written by every STEP launch: how heavy the env's control step was
   const float* packed;              // [JBP_SIZE] (shared model) or [N][JBP_SIZE] (per-env models)
   int per_env;
   int N, n_sub, step_limit, random_pose, obs_stride;
@@ -43,6 +45,10 @@ struct JbLaunchArgs {
   const float* actions;             // STEP
   float* obs; float* reward; int* step_type;
   int* rep_geom; float* rep_dist;   // CONTACTS: staging [N][4*JBQ_CAP]
+  // STEP: a control step is run as one or more launches ("segments") of sub_count sub-steps each, so that the slot order
+  // can be re-sorted in between (jb_sort.cu).  `first`: this launch starts the control step (pending episode resets happen
+  // here); `last`: it ends it (step counting, divergence check, reward, observation).  RESET launches set both.
+  int sub_count, first, last;
 };
 
 // two instantiations of jb_sim_kernel.cu: shared model / per-env models (see the head of that file)
@@ -50,4 +56,10 @@ cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st
 cudaError_t jb_configure_kernels(void);
 cudaError_t jb_launch_sim_perenv(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
 cudaError_t jb_configure_kernels_perenv(void);   // per device: opt in to the dynamic shared memory the per-env mode needs
+// jb_sort.cu: stable counting sort of the env ids by a small key of their last load record (the step kernel's slot order)
+#define JB_SORT_BUCKETS 16
+#define JB_SORT_MIN_ENVS (4 * 148 * JB_ENVS_PER_BLOCK)   /* four waves of full CTAs on a 148-SM part */
+#define JB_SEGMENT_SUBSTEPS 10
+int jb_sort_scratch_ints(int N);
+cudaError_t jb_sort_by_load(const int4* load, int N, int n_sub, int* perm_out, int* scratch, cudaStream_t st);
 #endif

@@ -148,7 +148,7 @@ __device__ __forceinline__ bool state_bad(const QState<float>& s) {
 }
 
 __device__ __forceinline__ void do_reset(const float* g, const JbDev& d, int e, int lane, QState<float>& s,
-                                         JbTarget<float>& tg, int task, bool live) {
+                                         JbTarget<float>& tg, int task, bool live, unsigned char reset_flag) {
   int ep = d.episode[e];
   jb_reset_env<float>(g, s, tg, task, d.random_pose, d.seed, d.env_id_offset + (unsigned)e, (unsigned)ep);
   s.qa = s.qb = s.va = s.vb = 0.f;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void do_reset(const float* g, const JbDev& d, int e, 
   if (lane == 0 && live) {
     d.episode[e] = ep + 1;
     d.step_count[e] = 0;
-    d.reset_next[e] = 0;
+    d.reset_next[e] = reset_flag;
     const int N = d.N;
     d.target[0 * N + e] = tg.x; d.target[1 * N + e] = tg.y; d.target[2 * N + e] = tg.qw; d.target[3 * N + e] = tg.qz;
   }
@@ -186,24 +186,26 @@ JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   const int lane = tid & 3;
   const int epb = blockDim.x >> 2;            // envs per CTA (the CTA size is chosen at launch, <= JB_BLOCK)
   const int e_raw = blockIdx.x * epb + (tid >> 2);
+  // slot -> env: the quads of the grid work on the envs in the order of d.perm (load-sorted, see jb_sort.cu), so that
+  // the heavy envs share warps and CTAs; padding quads past the end of the batch and envs not selected by a reset mask
+  // shadow a valid env and skip all stores (every thread runs the whole body: quad shuffles and warp votes need full warps)
+  const int slot = min(e_raw, d.N - 1);
+  const int e = d.perm ? d.perm[slot] : slot;
   // ---- packed model -> shared memory
   if (d.per_env) {
+    // 16-byte copies; each env's model starts JBP_ENV_STRIDE floats after the previous one (see jb_sim_common.cuh)
     const int e0 = blockIdx.x * epb;
     const int nenv = min(epb, d.N - e0);
-    // 16-byte copies; each env's model starts JBP_ENV_STRIDE floats after the previous one (see jb_sim_common.cuh)
-    const float4* src = reinterpret_cast<const float4*>(d.packed + (size_t)e0 * JBP_SIZE);
     float4* dst = reinterpret_cast<float4*>(jb_smem);
     for (int i = tid; i < nenv * (JBP_SIZE / 4); i += blockDim.x) {
-      const int env = i / (JBP_SIZE / 4), off = i - env * (JBP_SIZE / 4);
-      dst[env * (JBP_ENV_STRIDE / 4) + off] = src[i];
+      const int q = i / (JBP_SIZE / 4), off = i - q * (JBP_SIZE / 4);
+      const int env = d.perm ? d.perm[e0 + q] : e0 + q;
+      dst[q * (JBP_ENV_STRIDE / 4) + off] = reinterpret_cast<const float4*>(d.packed + (size_t)env * JBP_SIZE)[off];
     }
   } else {
     for (int i = tid; i < JBP_SIZE; i += blockDim.x) jb_smem[i] = d.packed[i];
   }
   __syncthreads();
-  // Every thread of the CTA runs the whole kernel body (the quad shuffles and warp votes need full warps): padding
-  // quads past the end of the batch and envs not selected by a reset mask shadow a valid env and skip all stores.
-  const int e = min(e_raw, d.N - 1);
   const float* P = d.per_env ? jb_smem + (tid >> 2) * JBP_ENV_STRIDE : jb_smem;
   QuadCommGPU cm;
 #ifdef JBQ_PHASE_TIMERS
@@ -214,16 +216,19 @@ JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   const int task = d.task[e];
   QState<float> s;
   JbTarget<float> tg;
-  const bool reset_now = a.mode == JB_MODE_RESET ? (!a.mask || a.mask[e]) : (a.mode == JB_MODE_STEP && d.reset_next[e]);
+  const unsigned char rflag = d.reset_next[e];
+  const bool reset_now = a.mode == JB_MODE_RESET ? (!a.mask || a.mask[e]) : (a.mode == JB_MODE_STEP && a.first && rflag == 1);
+  // an env that was reset by an earlier segment of this control step sits the remaining segments out
+  const bool sit_out = a.mode == JB_MODE_STEP && !a.first && rflag == 2;
   const bool live = e_raw < d.N && !(a.mode == JB_MODE_RESET && !reset_now);
-  int iters = 0, ncon_sum = 0, overflow = 0, nsub = 0;
+  int iters = 0, ncon_sum = 0, overflow = 0, nsub = 0, lane_load = 0;
   float ctrl = 0.f;
   if (reset_now) {
-    do_reset(P, d, e, lane, s, tg, task, live);
+    do_reset(P, d, e, lane, s, tg, task, live, a.last ? 0 : 2);
   } else {
     load_state(d, e, lane, s);
     tg.x = d.target[0 * N + e]; tg.y = d.target[1 * N + e]; tg.qw = d.target[2 * N + e]; tg.qz = d.target[3 * N + e];
-    if (a.mode == JB_MODE_STEP) { ctrl = a.actions[e]; nsub = d.n_sub; }
+    if (a.mode == JB_MODE_STEP && !sit_out) { ctrl = a.actions[e]; nsub = a.sub_count; }
   }
   // a reset / contact report runs one forward-only pass (mj_forward) for the warm start / the contact list.
   // Envs of one warp can be in different modes only at episode boundaries; the trip count is made warp-uniform.
@@ -242,41 +247,63 @@ JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
 #endif
     // an env that is resetting inside a stepping warp (episode boundary) just repeats zero-length sub-steps: they
     // leave the state untouched and recompute the same warm start
-    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, fwd_only, &iters, &ncon_sum, &overflow, want_rep ? &rep : nullptr);
+    jbq_substep<float, QuadCommGPU>(cm, P, lane, s, ctrl, fwd_only, &iters, &ncon_sum, &overflow, want_rep ? &rep : nullptr,
+                                    &lane_load);
   }
   if (a.mode == JB_MODE_CONTACTS) return;
+  // load record of these sub-steps (jb_sort.cu keys the next launch's slot order on it): the fullest lane's figures
+  int ld_n = lane_load & 0xfff, ld_3 = (lane_load >> 12) & 0xff, ld_2 = (lane_load >> 20) & 0xff;
+  int ld_last = (int)((unsigned)lane_load >> 28);
+#pragma unroll
+  for (int m = 1; m <= 2; m <<= 1) {
+    ld_n = max(ld_n, __shfl_xor_sync(0xffffffffu, ld_n, m));
+    ld_3 = max(ld_3, __shfl_xor_sync(0xffffffffu, ld_3, m));
+    ld_2 = max(ld_2, __shfl_xor_sync(0xffffffffu, ld_2, m));
+    ld_last = max(ld_last, __shfl_xor_sync(0xffffffffu, ld_last, m));
+  }
+  int bad = 0;
+  if (a.last) {                 // grid-uniform
+    if (!fwd_only) {            // mj_step1 of the last sub-step normalises qpos quaternions in place
+      float qn = rsqrtf(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
+      s.quat[0] *= qn; s.quat[1] *= qn; s.quat[2] *= qn; s.quat[3] *= qn;
+    }
+    // mj_checkPos / mj_checkVel: MuJoCo resets the data (dm_control raises PhysicsError); here the env restarts
+    bad = cm.isum(!fwd_only && state_bad(s) ? 1 : 0);
+    if (bad) do_reset(P, d, e, lane, s, tg, task, live, 0);
+  }
+  if (!live) return;
   if (fwd_only) {
-    if (live) {
+    if (reset_now) {
       store_state(d, e, lane, s);
       if (lane == 0) {
         write_obs(P, d, e, s, task, tg, a.obs, nullptr);
         if (a.reward) a.reward[e] = 0.f;
         if (a.step_type) a.step_type[e] = JB_STEP_FIRST;
       }
+    } else if (a.last && lane == 0) {
+      d.reset_next[e] = 0;      // sat out the control step it was reset in: back to stepping
     }
     return;
   }
-  {   // mj_step1 of the last sub-step normalises qpos quaternions in place
-    float qn = rsqrtf(s.quat[0] * s.quat[0] + s.quat[1] * s.quat[1] + s.quat[2] * s.quat[2] + s.quat[3] * s.quat[3]);
-    s.quat[0] *= qn; s.quat[1] *= qn; s.quat[2] *= qn; s.quat[3] *= qn;
-  }
-  // mj_checkPos / mj_checkVel: MuJoCo resets the data (dm_control raises PhysicsError); here the env restarts
-  const int bad = cm.isum(state_bad(s) ? 1 : 0);
-  if (bad) do_reset(P, d, e, lane, s, tg, task, live);
-  if (!live) return;
   if (overflow) atomicAdd(&d.counters[3], (unsigned long long)overflow);     // rare: any lane that ran out of slots
   store_state(d, e, lane, s);
   if (lane == 0) {
-    int sc = bad ? 0 : d.step_count[e] + 1;
-    d.step_count[e] = sc;
-    int st = JB_STEP_MID;
-    if (d.step_limit > 0 && sc >= d.step_limit) { st = JB_STEP_LAST; d.reset_next[e] = 1; }
-    write_obs(P, d, e, s, task, tg, a.obs, a.reward);
-    if (a.step_type) a.step_type[e] = st;
     atomicAdd(&d.counters[1], (unsigned long long)iters);
     atomicAdd(&d.counters[2], (unsigned long long)ncon_sum);
-    if (bad) atomicAdd(&d.counters[4], 1ull);
-    if (e == 0) atomicAdd(&d.counters[0], (unsigned long long)d.n_sub * (unsigned long long)N);
+    if (e == 0) atomicAdd(&d.counters[0], (unsigned long long)a.sub_count * (unsigned long long)N);
+    if (d.load) d.load[e] = make_int4(ld_n, ld_3, ld_2, iters | (ld_last << 16));
+    if (a.last) {
+      int sc = bad ? 0 : d.step_count[e] + 1;
+      d.step_count[e] = sc;
+      int st = JB_STEP_MID;
+      if (d.step_limit > 0 && sc >= d.step_limit) { st = JB_STEP_LAST; d.reset_next[e] = 1; }
+      write_obs(P, d, e, s, task, tg, a.obs, a.reward);
+      // a diverged env has just been restarted: its caller sees the episode boundary (FIRST, reward 0, the observation
+      // of the fresh episode) -- dm_control raises PhysicsError here and the caller resets
+      if (bad) { st = JB_STEP_FIRST; if (a.reward) a.reward[e] = 0.f; }
+      if (a.step_type) a.step_type[e] = st;
+      if (bad) atomicAdd(&d.counters[4], 1ull);
+    }
   }
 #ifdef JBQ_PHASE_TIMERS
   if ((tid & 31) == 0) for (int i = 1; i < 8; i++) atomicAdd(&d.counters[8 + i], (unsigned long long)cm.acc[i]);

@@ -131,19 +131,19 @@ JB_HD JbPhilox jb_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uin
 }
 JB_HD float jb_u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }   // [0, 1)
 
-// Episode initial conditions (jitterbug.py:601-666): returns the reset state and target for (global env id, episode)
-// Fills the root part of the state (pos, quat, zero velocities / motor / warm start); the caller zeroes its leg state.
+// Episode initial conditions (jitterbug.py:601-666) as a function of the six uniforms in [0, 1) the reference draws:
+// u[0] -> angle = self.random.uniform(0, 2*pi), u[1] -> radius = self.random.uniform(.05, .2), u[2] -> yaw =
+// np.random.uniform(0, 2*pi), u[3] -> rotation_angle = np.random.random() * 2*pi, u[4], u[5] -> rotation axis x, y =
+// np.random.random(2) * .05 - .025.  Fills the root part of the state (pos, quat, zero velocities / motor); the caller
+// zeroes its leg state and the warm start.
 template <typename T, typename S>
-JB_HD void jb_reset_env(const T* g, S& s, JbTarget<T>& tg, int task, int random_pose,
-                        uint64_t seed, uint32_t env_gid, uint32_t episode) {
-  JbPhilox r0 = jb_philox(env_gid, episode, 0u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  JbPhilox r1 = jb_philox(env_gid, episode, 1u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
-  T angle = (T)(2 * JB_PI) * (T)jb_u01(r0.v[0]);                 // self.random.uniform(0, 2*pi)
-  T radius = (T)0.05 + (T)0.15 * (T)jb_u01(r0.v[1]);             // self.random.uniform(.05, .2)
-  T yaw = (T)(2 * JB_PI) * (T)jb_u01(r0.v[2]);                   // np.random.uniform(0, 2*pi)
-  T rot = (T)(2 * JB_PI) * (T)jb_u01(r0.v[3]);                   // np.random.random() * 2*pi
-  T ax = (T)0.05 * (T)jb_u01(r1.v[0]) - (T)0.025;                // np.random.random(2) * .05 - .025
-  T ay = (T)0.05 * (T)jb_u01(r1.v[1]) - (T)0.025;
+JB_HD void jb_reset_from_uniforms(const T* g, S& s, JbTarget<T>& tg, int task, int random_pose, const T* u) {
+  T angle = (T)(2 * JB_PI) * u[0];
+  T radius = (T)0.05 + (T)0.15 * u[1];
+  T yaw = (T)(2 * JB_PI) * u[2];
+  T rot = (T)(2 * JB_PI) * u[3];
+  T ax = (T)0.05 * u[4] - (T)0.025;
+  T ay = (T)0.05 * u[5] - (T)0.025;
   tg.x = g[G_TGT0]; tg.y = g[G_TGT0 + 1]; tg.qw = (T)1; tg.qz = (T)0;
   T sa, ca;
   if (task == JB_TASK_MOVE_TO_POSITION || task == JB_TASK_MOVE_TO_POSE) {
@@ -164,6 +164,18 @@ JB_HD void jb_reset_env(const T* g, S& s, JbTarget<T>& tg, int task, int random_
   s.qm = 0; s.vm = 0; s.rev = 0;
 #pragma unroll
   for (int i = 0; i < 3; i++) { s.vlin[i] = 0; s.w[i] = 0; }
+}
+
+// The uniforms come from Philox4x32-10 streams keyed by (seed, global env id, episode): the reference's two numpy
+// generators cannot be reproduced bit for bit, the distributions are.
+template <typename T, typename S>
+JB_HD void jb_reset_env(const T* g, S& s, JbTarget<T>& tg, int task, int random_pose,
+                        uint64_t seed, uint32_t env_gid, uint32_t episode) {
+  JbPhilox r0 = jb_philox(env_gid, episode, 0u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  JbPhilox r1 = jb_philox(env_gid, episode, 1u, 0x4A42u, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const T u[6] = {(T)jb_u01(r0.v[0]), (T)jb_u01(r0.v[1]), (T)jb_u01(r0.v[2]), (T)jb_u01(r0.v[3]),
+                  (T)jb_u01(r1.v[0]), (T)jb_u01(r1.v[1])};
+  jb_reset_from_uniforms<T, S>(g, s, tg, task, random_pose, u);
 }
 
 // ------------------------------------------------------------------------------------------------ heuristic policies

@@ -31,6 +31,26 @@ def get_model_and_assets():
         return f.read(), {}
 
 
+def tolerance(x, bounds=(0.0, 0.0), margin=0.0, sigmoid='gaussian', value_at_margin=0.1):
+    """Scalar ``dm_control.utils.rewards.tolerance`` for the three sigmoids the Jitterbug rewards use (call sites
+    jitterbug.py:846, :860, :874, :884): 1 inside ``bounds``, decaying to ``value_at_margin`` one ``margin`` outside."""
+    lower, upper = bounds
+    if lower <= x <= upper:
+        return 1.0
+    if margin == 0:
+        return 0.0
+    d = (lower - x if x < lower else x - upper) / margin
+    if sigmoid == 'gaussian':
+        return float(np.exp(-0.5 * (d * np.sqrt(-2 * np.log(value_at_margin))) ** 2))
+    if sigmoid == 'linear':
+        sx = d * (1 - value_at_margin)
+        return float(1 - sx) if abs(sx) < 1 else 0.0
+    if sigmoid == 'cosine':
+        sx = d * np.arccos(2 * value_at_margin - 1) / np.pi
+        return float((1 + np.cos(np.pi * sx)) / 2) if abs(sx) < 1 else 0.0
+    raise ValueError("Unknown sigmoid type {!r}".format(sigmoid))
+
+
 def _quat2mat(q):
     return mjcf.quat2mat(np.asarray(q, dtype=np.float64))
 
@@ -43,6 +63,16 @@ class Physics:
         self.model = model if model is not None else batched.model
         self._cache = None
 
+    @classmethod
+    def from_state(cls, model, qpos, qvel, target=(0.0, 0.0, 1.0, 0.0)):
+        """Detached host-side physics view of a given state (``target`` = x, y, quat_w, quat_z): the helpers and the
+        task's ``get_observation`` / ``get_reward`` then work without a simulator (analysis, tests)."""
+        ph = cls.__new__(cls)
+        ph._b, ph._i, ph.model = None, 0, model
+        ph._cache = (np.asarray(qpos, dtype=np.float64).copy(), np.asarray(qvel, dtype=np.float64).copy(),
+                     np.asarray(target, dtype=np.float64).copy())
+        return ph
+
     # ---- raw state (host copies, float64)
     def _state(self):
         if self._cache is None:
@@ -53,7 +83,8 @@ class Physics:
         return self._cache
 
     def _invalidate(self):
-        self._cache = None
+        if self._b is not None:
+            self._cache = None
 
     @property
     def qpos(self):
@@ -130,6 +161,10 @@ class Physics:
         angle = angle - 2 * np.pi * np.ceil((angle - np.pi) / (2 * np.pi))
         return np.array([angle])
 
+    def jitterbug_upright(self):
+        """``physics.named.data.xmat['jitterbug', 'zz']`` (jitterbug.py:886): body z axis . world z."""
+        return float(_quat2mat(self.jitterbug_position_quat())[2, 2])
+
 
 class Jitterbug:
     """The task description (constructor kwargs and normalisation tables of ``jitterbug.Jitterbug``)."""
@@ -160,6 +195,63 @@ class Jitterbug:
     @staticmethod
     def _norm(v, min, max):  # noqa: A002 - reference signature
         return (v - min) / (max - min) * 2.0 - 1.0
+
+    # ---- host-callable twins of the task methods (jitterbug.py:673-763, :840-925).  The batched simulator computes the
+    # same quantities on the device (csrc/jb_task.cuh); these serve single-state analysis through ``env.task``.
+    def get_observation(self, physics):
+        """Returns an observation of the state and the target position (always normalised, App. C3)."""
+        na, nt = Jitterbug._NORM_ALL, Jitterbug._NORM_TASKS[self.task]
+        obs = collections.OrderedDict()
+        obs['position'] = Jitterbug._norm(physics.jitterbug_position(), na[0:7, 0], na[0:7, 1])
+        obs['velocity'] = Jitterbug._norm(physics.jitterbug_velocity(), na[7:13, 0], na[7:13, 1])
+        obs['motor_position'] = Jitterbug._norm(physics.motor_position(), na[13, 0], na[13, 1])
+        obs['motor_velocity'] = Jitterbug._norm(physics.motor_velocity(), na[14, 0], na[14, 1])
+        if self.task in ("face_direction", "move_in_direction"):
+            obs['angle_to_target'] = Jitterbug._norm(physics.angle_jitterbug_to_target(), nt[0, 0], nt[0, 1])
+        if self.task == "move_in_direction":
+            obs['speed_in_target_frame'] = Jitterbug._norm(physics.jitterbug_velocity_in_target_frame(), nt[1:, 0], nt[1:, 1])
+        if self.task in ("move_to_position", "move_to_pose"):
+            obs['target_in_jitterbug_frame'] = Jitterbug._norm(physics.target_position_in_jitterbug_frame(),
+                                                               nt[0:3, 0], nt[0:3, 1])
+        if self.task == "move_to_pose":
+            obs['angle_to_target'] = Jitterbug._norm(physics.angle_jitterbug_to_target(), nt[3, 0], nt[3, 1])
+        return obs
+
+    def obsdict2vec(self, obs):
+        """Observation dict -> (vector, column names), jitterbug.py:765-838."""
+        columns = ["X", "Y", "Z", "QuatX", "QuatY", "QuatZ", "QuatW", "VelX", "VelY", "VelZ", "VelRoll", "VelPitch",
+                   "VelYaw", "MotorYaw", "MotorVelYaw"]
+        extra = {"face_direction": ["TargetYaw"], "move_in_direction": ["TargetYaw", "TargetVelX", "TargetVelY", "TargetVelZ"],
+                 "move_to_position": ["TargetX", "TargetY", "TargetZ"],
+                 "move_to_pose": ["TargetX", "TargetY", "TargetZ", "TargetYaw"]}.get(self.task, [])
+        return np.concatenate([np.ravel(v) for v in obs.values()]), columns + extra
+
+    def heading_reward(self, physics):
+        return tolerance(physics.angle_jitterbug_to_target()[0], bounds=(0, 0), margin=np.pi / 2, value_at_margin=0,
+                         sigmoid='cosine')
+
+    def velocity_reward(self, physics):
+        return tolerance(physics.jitterbug_velocity_in_target_frame()[0], bounds=(TARGET_SPEED, float('inf')),
+                         margin=TARGET_SPEED, value_at_margin=0, sigmoid='linear')
+
+    def position_reward(self, physics):
+        return tolerance(np.linalg.norm(physics.target_position_in_jitterbug_frame()), bounds=(0, 0), margin=0.05)
+
+    def upright_reward(self, physics):
+        return tolerance(physics.jitterbug_upright(), bounds=(1, 1), margin=0.5)
+
+    def get_reward(self, physics):
+        if self.task == "move_from_origin":
+            r = 1 - self.position_reward(physics)
+        elif self.task == "face_direction":
+            r = self.heading_reward(physics)
+        elif self.task == "move_in_direction":
+            r = self.velocity_reward(physics)
+        elif self.task == "move_to_position":
+            r = self.position_reward(physics)
+        else:
+            r = self.position_reward(physics) * self.heading_reward(physics)
+        return r * self.upright_reward(physics)
 
 
 class Environment:

@@ -124,6 +124,19 @@ def reset_states(seed, env_ids, episode, task, random_pose, packed=None):
     return out
 
 
+def reset_from_uniforms(u, task, random_pose, packed):
+    """Host run of the device reset mapping from given uniforms u[n, 6] (dtype follows ``packed``): rows of
+    (quat w,x,y,z, target x, y, qw, qz)."""
+    L = qlib()
+    dt = packed.dtype
+    uu = np.ascontiguousarray(u, dtype=dt)
+    out = np.zeros((len(uu), 8), dtype=dt)
+    fn = L.hq_reset_from_uniforms_f64 if dt == np.float64 else L.hq_reset_from_uniforms_f32
+    fn(packed.ctypes.data_as(C.c_void_p), uu.ctypes.data_as(C.c_void_p), C.c_int(len(uu)), C.c_int(task), C.c_int(random_pose),
+       out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def obs_reward(qpos, qvel, task, target, packed=None):
     L = qlib()
     P = default_packed_f32() if packed is None else packed

@@ -161,6 +161,25 @@ void hq_reset_states(const float* P, unsigned long long seed, const unsigned* en
     out[8 * i + 4] = tg.x; out[8 * i + 5] = tg.y; out[8 * i + 6] = tg.qw; out[8 * i + 7] = tg.qz;
   }
 }
+// the reset mapping alone, from given uniforms u[n][6] (double and float instantiations)
+void hq_reset_from_uniforms_f32(const float* P, const float* u, int n, int task, int random_pose, float* out) {
+  for (int i = 0; i < n; i++) {
+    QState<float> s;
+    JbTarget<float> tg;
+    jb_reset_from_uniforms<float>(P, s, tg, task, random_pose, u + 6 * i);
+    for (int k = 0; k < 4; k++) out[8 * i + k] = s.quat[k];
+    out[8 * i + 4] = tg.x; out[8 * i + 5] = tg.y; out[8 * i + 6] = tg.qw; out[8 * i + 7] = tg.qz;
+  }
+}
+void hq_reset_from_uniforms_f64(const double* P, const double* u, int n, int task, int random_pose, double* out) {
+  for (int i = 0; i < n; i++) {
+    QState<double> s;
+    JbTarget<double> tg;
+    jb_reset_from_uniforms<double>(P, s, tg, task, random_pose, u + 6 * i);
+    for (int k = 0; k < 4; k++) out[8 * i + k] = s.quat[k];
+    out[8 * i + 4] = tg.x; out[8 * i + 5] = tg.y; out[8 * i + 6] = tg.qw; out[8 * i + 7] = tg.qz;
+  }
+}
 // host instantiation of the device obs/reward and heuristic code for one env
 int hq_obs_reward(const float* P, const float* qpos, const float* qvel, int task, const float* tgt, float* obs, float* rew) {
   QState<float> s;
