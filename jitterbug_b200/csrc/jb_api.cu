@@ -236,15 +236,18 @@ static int sim_fill(JbSim* s, const JbSimConfig* cfg, const int32_t* task_ids_ho
   CUDA_TRY(cudaMemset(d.load, 0, N * sizeof(int4)));
   CUDA_TRY(cudaMalloc(&s->perm_buf, 2 * N * sizeof(int)));
   CUDA_TRY(cudaMalloc(&s->sort_scratch, (size_t)jb_sort_scratch_ints((int)N) * sizeof(int)));
-  d.perm = nullptr;                      // identity until the first sort
+  jb_iota_kernel<<<grid_of((int)N), JB_BLOCK>>>(s->perm_buf, (int)N);      // identity until the first sort
+  CUDA_TRY(cudaGetLastError());
   s->perm_cur = 0;
   // Sorting pays when the grid is several waves deep (the heavy envs then fill whole CTAs of their own); small batches
   // (parity configurations, the single-env adapter) keep slot i = env i and one launch per control step.
   s->auto_sort = N >= (size_t)JB_SORT_MIN_ENVS ? 1 : 0;
+  d.perm = s->auto_sort ? s->perm_buf : nullptr;
   // An env's load is persistent over ~10 sub-steps, much less over 50 (measured: profiles/README.md, round 2): the
   // control step is cut into launches of JB_SEGMENT_SUBSTEPS sub-steps and the order re-sorted after each.
   s->seg_sub = JB_SEGMENT_SUBSTEPS;
   if (const char* e = getenv("JBSIM_SEGMENT")) s->seg_sub = atoi(e) > 0 ? atoi(e) : (1 << 30);
+  CUDA_TRY(cudaDeviceSynchronize());      // the initialisation above ran on the default stream; callers bring their own
   return 0;
 }
 
@@ -347,19 +350,25 @@ int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* rewar
   cudaStream_t st = (cudaStream_t)stream;
   JbLaunchArgs a = {JB_MODE_STEP, nullptr, actions_dev, obs_dev, reward_dev, step_type_dev, nullptr, nullptr, 0, 0, 0};
   const int n_sub = s->d.n_sub, seg = s->auto_sort ? s->seg_sub : n_sub;
+  const size_t N = s->d.N;
+  // Slot order: segment i reads perm buffer i & 1 and the sort that follows it writes the other one; every control step
+  // starts from buffer 0 (an odd number of segments ends with a device copy 1 -> 0), so the sequence of launches and
+  // pointers is the same for every step -- a step can be captured in a CUDA graph and replayed.
+  int cur = 0;
   for (int k0 = 0; k0 < n_sub; k0 += seg) {
     a.sub_count = n_sub - k0 < seg ? n_sub - k0 : seg;
     a.first = k0 == 0;
     a.last = k0 + a.sub_count >= n_sub;
+    if (s->auto_sort) s->d.perm = s->perm_buf + (size_t)cur * N;
     CUDA_TRY(launch(s, a, st));
     if (s->auto_sort) {
-      // slot order of the NEXT launch from this segment's load records (jb_sort.cu); double-buffered: the kernel just
-      // enqueued still reads the current order
-      int* next = s->perm_buf + (size_t)(s->perm_cur ^ 1) * s->d.N;
-      CUDA_TRY(jb_sort_by_load(s->d.load, s->d.N, a.sub_count, next, s->sort_scratch, st));
-      s->perm_cur ^= 1;
-      s->d.perm = next;
+      CUDA_TRY(jb_sort_by_load(s->d.load, s->d.N, a.sub_count, s->perm_buf + (size_t)(cur ^ 1) * N, s->sort_scratch, st));
+      cur ^= 1;
     }
+  }
+  if (s->auto_sort) {
+    if (cur == 1) CUDA_TRY(cudaMemcpyAsync(s->perm_buf, s->perm_buf + N, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    s->d.perm = s->perm_buf;
   }
   return 0;
 }
@@ -509,14 +518,20 @@ int jb_sim_get_load(JbSim* s, int32_t* load_dev, void* stream) {
 int jb_sim_set_slot_order(JbSim* s, int mode, const int32_t* perm_dev, void* stream) {
   if (!s) return fail("jb_sim_set_slot_order: null sim");
   JB_GUARD(s);
-  if (mode == JB_ORDER_AUTO) { s->auto_sort = 1; return 0; }      // also for batches below JB_SORT_MIN_ENVS (tests)
+  if (mode == JB_ORDER_AUTO) {             // also for batches below JB_SORT_MIN_ENVS (tests)
+    if (!s->auto_sort && !s->d.perm) {
+      jb_iota_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->perm_buf, s->d.N);
+      CUDA_TRY(cudaGetLastError());
+    }
+    s->auto_sort = 1;
+    s->d.perm = s->perm_buf;
+    return 0;
+  }
   s->auto_sort = 0;
   if (mode == JB_ORDER_IDENTITY) { s->d.perm = nullptr; return 0; }
   if (mode != JB_ORDER_EXPLICIT || !perm_dev) return fail("jb_sim_set_slot_order: bad mode / null permutation");
-  int* next = s->perm_buf + (size_t)(s->perm_cur ^ 1) * s->d.N;
-  CUDA_TRY(cudaMemcpyAsync(next, perm_dev, (size_t)s->d.N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
-  s->perm_cur ^= 1;
-  s->d.perm = next;
+  CUDA_TRY(cudaMemcpyAsync(s->perm_buf, perm_dev, (size_t)s->d.N * sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  s->d.perm = s->perm_buf;
   return 0;
 }
 

@@ -221,6 +221,8 @@ JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchA
   // an env that was reset by an earlier segment of this control step sits the remaining segments out
   const bool sit_out = a.mode == JB_MODE_STEP && !a.first && rflag == 2;
   const bool live = e_raw < d.N && !(a.mode == JB_MODE_RESET && !reset_now);
+  // a masked reset usually selects few envs (episode boundaries of a VecEnv loop): CTAs without one leave at once
+  if (a.mode == JB_MODE_RESET && a.mask && !__syncthreads_or(live ? 1 : 0)) return;
   int iters = 0, ncon_sum = 0, overflow = 0, nsub = 0, lane_load = 0;
   float ctrl = 0.f;
   if (reset_now) {

@@ -24,12 +24,20 @@ def shard_envs(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     return offset, count
 
 
-def gather_episode_stats(returns: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> Dict[str, float]:
-    """Global mean / std / min / max / count of per-env episode returns across all ranks (one small all-reduce each)."""
-    r = returns.detach().double().reshape(-1)
-    sums = torch.stack([r.sum(), (r * r).sum(), torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device)])
-    lo = r.min() if r.numel() else torch.tensor(float("inf"), dtype=torch.float64, device=r.device)
-    hi = r.max() if r.numel() else torch.tensor(float("-inf"), dtype=torch.float64, device=r.device)
+def gather_episode_stats(returns: Optional[torch.Tensor], group: Optional[dist.ProcessGroup] = None, moments=None) -> Dict[str, float]:
+    """Global mean / std / min / max / count of episode returns across all ranks (one small all-reduce each).
+
+    Either ``returns`` (a tensor of per-episode returns held by this rank) or ``moments`` = (count, sum, sum of
+    squares, min, max) accumulated on the device by a running monitor (``rollout.VecJitterbugEnv``)."""
+    if moments is None:
+        r = returns.detach().double().reshape(-1)
+        dev = r.device
+        cnt, s1, s2 = torch.tensor(float(r.numel()), dtype=torch.float64, device=dev), r.sum(), (r * r).sum()
+        lo = r.min() if r.numel() else torch.tensor(float("inf"), dtype=torch.float64, device=dev)
+        hi = r.max() if r.numel() else torch.tensor(float("-inf"), dtype=torch.float64, device=dev)
+    else:
+        cnt, s1, s2, lo, hi = [m.detach().double().clone() for m in moments]
+    sums = torch.stack([s1, s2, cnt])
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)

@@ -257,8 +257,9 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
 
     comp = root.find("compiler")
     coordinate = comp.attrib.get("coordinate", "local") if comp is not None else "local"
-    if coordinate != "global":
-        raise NotImplementedError("only coordinate=\"global\" models (the Jitterbug family) are supported")
+    if coordinate not in ("global", "local"):
+        raise NotImplementedError("unknown <compiler coordinate>")
+    local = coordinate == "local"      # e.g. to_local_xml()'s output: frames are composed into world frames while walking
 
     opt = root.find("option")
     timestep = float(opt.attrib.get("timestep", 0.002)) if opt is not None else 0.002
@@ -276,6 +277,15 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
     geoms = []   # dicts
     joints = []
 
+    def to_world(bidx, pos, quat=None, vec=None):
+        """local-coordinate models: compose an element's body-relative pose / direction with its body's world frame"""
+        if not local:
+            return pos, quat, vec
+        b = bodies[bidx]
+        rb = quat2mat(b.quat)
+        return (b.pos + rb @ pos if pos is not None else None, quat_mul(b.quat, quat) if quat is not None else None,
+                rb @ vec if vec is not None else None)
+
     def add_geom(el, bidx):
         gtype = _GEOM_TYPES[el.attrib.get("type", "sphere")]
         size = np.zeros(3)
@@ -283,14 +293,17 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
         size[:len(s)] = s
         if "fromto" in el.attrib:
             ft = _floats(el.attrib["fromto"])
-            vec = ft[0:3] - ft[3:6]          # MuJoCo: z axis points from "to" to "from"
+            p_from, _, _ = to_world(bidx, ft[0:3])
+            p_to, _, _ = to_world(bidx, ft[3:6])
+            vec = p_from - p_to              # MuJoCo: z axis points from "to" to "from"
             size[1] = 0.5 * np.linalg.norm(vec)
-            pos = 0.5 * (ft[0:3] + ft[3:6])
+            pos = 0.5 * (p_from + p_to)
             quat = z2quat(vec)
         else:
             pos = _floats(el.attrib.get("pos", "0 0 0"))
             quat = _floats(el.attrib.get("quat", "1 0 0 0"))
             quat = quat / np.linalg.norm(quat)
+            pos, quat, _ = to_world(bidx, pos, quat)
         geoms.append(dict(
             name=el.attrib.get("name", ""), type=gtype, body=bidx, size=size, pos=pos, quat=quat,
             density=float(el.attrib.get("density", default_density)), density_default=int("density" not in el.attrib),
@@ -300,10 +313,11 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
 
     def add_joint(el, bidx):
         jtype = {"free": JNT_FREE, "hinge": JNT_HINGE}[el.attrib.get("type", "hinge")]
+        pos, _, axis = to_world(bidx, _floats(el.attrib.get("pos", "0 0 0")), None, _floats(el.attrib.get("axis", "0 0 1")))
         joints.append(dict(
             name=el.attrib.get("name", ""), type=jtype, body=bidx,
-            pos=_floats(el.attrib.get("pos", "0 0 0")) if jtype != JNT_FREE else None,
-            axis=_floats(el.attrib.get("axis", "0 0 1")),
+            pos=pos if jtype != JNT_FREE else None,
+            axis=axis,
             stiffness=float(el.attrib.get("stiffness", 0.0)),
             damping=float(el.attrib.get("damping", 0.0)),
         ))
@@ -319,10 +333,14 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
         for child in el:
             if child.tag == "body":
                 b = _Body(child.attrib.get("name", ""), bidx)
-                if "pos" in child.attrib:
-                    b.pos = _floats(child.attrib["pos"])
+                if "pos" in child.attrib or local:
+                    b.pos = _floats(child.attrib.get("pos", "0 0 0"))
                     b.quat = _floats(child.attrib.get("quat", "1 0 0 0"))
                     b.quat = b.quat / np.linalg.norm(b.quat)
+                    if local:
+                        par = bodies[bidx]
+                        b.pos = par.pos + quat2mat(par.quat) @ b.pos
+                        b.quat = quat_mul(par.quat, b.quat)
                 bodies.append(b)
                 walk(child, len(bodies) - 1)
 
@@ -538,6 +556,73 @@ def compile_xml(xml: Optional[str] = None, *, path: Optional[str] = None) -> Com
     )
     _set_const(model)
     return model
+
+
+# --------------------------------------------------------------------------- export
+def to_local_xml(m: CompiledModel) -> str:
+    """The compiled model as a LOCAL-coordinate MJCF that current MuJoCo releases load.
+
+    ``jitterbug.xml`` uses ``<compiler coordinate="global"/>`` (jitterbug_dmc/jitterbug.xml:4), which MuJoCo removed in
+    2.3.4, so ``pip install mujoco`` cannot load the reference model.  This writes the same model with every frame
+    expressed in its parent (what MuJoCo 2.0's compiler produced internally): body frames as compiled here (bodies
+    without ``pos`` in the global file sit at their inertial frame), geoms by type / size / pos / quat instead of
+    ``fromto``, unit hinge axes, MuJoCo 2.0's option defaults spelled out.  Masses and inertias are NOT written:
+    MuJoCo recomputes them from the geoms, which is one of the things ``tests/test_mujoco_parity.py`` compares.
+    The ``coordinate`` attribute itself is omitted (local is the only mode left).
+    """
+    def f(a):
+        return " ".join(repr(float(x)) for x in np.atleast_1d(a))
+
+    gtypes = {v: k for k, v in _GEOM_TYPES.items()}
+    children = {b: [c for c in range(1, m.nbody) if m.body_parentid[c] == b] for b in range(m.nbody)}
+    out = ['<mujoco model="jitterbug_local">',
+           '  <compiler angle="radian" inertiafromgeom="true"/>',
+           f'  <option timestep="{f(m.timestep)}" gravity="{f(m.gravity)}" integrator="Euler" cone="pyramidal" '
+           f'solver="Newton" iterations="{int(m.iterations)}" tolerance="{f(m.tolerance)}" impratio="{f(m.impratio)}"/>',
+           '  <worldbody>']
+
+    def geom_xml(g, ind):
+        t = int(m.geom_type[g])
+        nsize = {GEOM_PLANE: 3, GEOM_SPHERE: 1, GEOM_CYLINDER: 2, GEOM_ELLIPSOID: 3, GEOM_BOX: 3}[t]
+        name = f' name="{m.geom_names[g]}"' if m.geom_names[g] else ""
+        dens = "" if t == GEOM_PLANE else f' density="{f(m.geom_density[g])}"'
+        return (f'{ind}<geom{name} type="{gtypes[t]}" size="{f(m.geom_size[g][:nsize])}" pos="{f(m.geom_pos[g])}" '
+                f'quat="{f(m.geom_quat[g])}"{dens} contype="{int(m.geom_contype[g])}" '
+                f'conaffinity="{int(m.geom_conaffinity[g])}" condim="{int(m.geom_condim[g])}" '
+                f'friction="{f(m.geom_friction[g])}" solref="{f(m.geom_solref[g])}" solimp="{f(m.geom_solimp[g])}" '
+                f'margin="{f(m.geom_margin[g])}" gap="{f(m.geom_gap[g])}"/>')
+
+    def body_xml(b, ind):
+        for g in range(m.ngeom):
+            if m.geom_bodyid[g] == b:
+                out.append(geom_xml(g, ind))
+        for j in range(m.njnt):
+            if m.jnt_bodyid[j] == b:
+                if m.jnt_type[j] == JNT_FREE:
+                    out.append(f'{ind}<joint name="{m.jnt_names[j]}" type="free"/>')
+                else:
+                    d = int(m.jnt_dofadr[j])
+                    out.append(f'{ind}<joint name="{m.jnt_names[j]}" type="hinge" pos="{f(m.jnt_pos[j])}" '
+                               f'axis="{f(m.jnt_axis[j])}" stiffness="{f(m.jnt_stiffness[j])}" '
+                               f'damping="{f(m.dof_damping[d])}" springref="0"/>')
+        for c in children[b]:
+            out.append(f'{ind}<body name="{m.body_names[c]}" pos="{f(m.body_pos[c])}" quat="{f(m.body_quat[c])}">')
+            body_xml(c, ind + "  ")
+            out.append(f'{ind}</body>')
+
+    body_xml(0, "    ")
+    out.append('  </worldbody>')
+    if m.sensor_body >= 0:
+        out += ['  <sensor>', f'    <framelinvel name="jitterbug_framelinvel" objtype="body" '
+                              f'objname="{m.body_names[m.sensor_body]}"/>', '  </sensor>']
+    out.append('  <actuator>')
+    for a in range(m.nu):
+        out.append(f'    <general joint="{m.jnt_names[int(m.actuator_trnid[a])]}" '
+                   f'ctrllimited="{"true" if m.actuator_ctrllimited[a] else "false"}" ctrlrange="{f(m.actuator_ctrlrange[a])}" '
+                   f'gear="{f(m.actuator_gear[a])}" dyntype="none" gaintype="fixed" gainprm="{f(m.actuator_gainprm[a])}" '
+                   f'biastype="affine" biasprm="{f(m.actuator_biasprm[a])}"/>')
+    out += ['  </actuator>', '</mujoco>', '']
+    return "\n".join(out)
 
 
 # --------------------------------------------------------------------------- numpy kinematics / Jacobians (compiler + tests)

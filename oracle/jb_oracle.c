@@ -1056,6 +1056,74 @@ static void* rolloutWorker(void* arg) {
   return 0;
 }
 
+/* heuristic_policies.py:6-136 on the normalised observation vector (layout of jbo_task_obs_reward), fp64 */
+static double hFace(double a) { double v = 3 * a / PI; return 0.9 * (v > 1 ? 1 : (v < -1 ? -1 : v)); }
+static double hForward(double motor_angle, double motor_vel, double offset) {
+  const double kick = PI / 4, speed = 0.3;                               /* move_forward(), :29-56 */
+  if (motor_angle < offset - kick) return speed;
+  if (motor_angle > offset + kick) return -speed;
+  return motor_vel > 0 ? speed : -speed;
+}
+static double hOrient(double a, double* offset) {                        /* optimal_orientation_to_move(), :119-136 */
+  *offset = 0;
+  if (a >= -45 * PI / 180 && a <= 45 * PI / 180) return a;
+  if (a > 45 * PI / 180 && a <= PI) { *offset = PI / 2; return fabs(fabs(a) - 90 * PI / 180); }
+  if (a >= -PI && a < -45 * PI / 180) { *offset = -PI / 2; return -fabs(fabs(a) - 90 * PI / 180); }
+  return a;
+}
+double jbo_heuristic(int task, const double* obs) {
+  const double thr = 20 * PI / 180;
+  double ma = obs[13], mv = obs[14], a, off;
+  if (task == 0) return hForward(ma, mv, 0);                             /* move_from_origin, :59-61 */
+  if (task == 1) return hFace(obs[15]);                                  /* face_direction, :6-26 */
+  if (task == 2) {                                                       /* move_in_direction, :64-78 */
+    a = hOrient(obs[15], &off);
+    return fabs(a) > thr ? hFace(a) : hForward(ma, mv, off);
+  }
+  a = atan2(obs[15], -obs[16]);
+  if (task == 3) {                                                       /* move_to_position, :81-95 */
+    a = hOrient(a, &off);
+    return fabs(a) > thr ? hFace(a) : hForward(ma, mv, off);
+  }
+  if (fabs(a) > thr) return hFace(a);                                    /* move_to_pose, :98-117 */
+  if (sqrt(obs[15] * obs[15] + obs[16] * obs[16]) > 0.01) return hForward(ma, mv, 0);
+  return hFace(obs[18]);
+}
+
+/* closed-loop rollouts under the heuristic policy of `task` (benchmarks/evaluate_policy.py:10-35: act on the current
+ * observation, step, record the reward); the datas must have been forwarded (jbo_forward) */
+static void* heuristicWorker(void* arg) {
+  RolloutJob* j = (RolloutJob*)arg;
+  int e, s;
+  for (e = j->tid; e < j->nenv; e += j->nthreads) {
+    double obs[32], rew = 0, act;
+    jbo_task_obs_reward(&j->models[e], &j->datas[e], j->task, obs, &rew);
+    for (s = 0; s < j->nsteps; s++) {
+      act = jbo_heuristic(j->task, obs);
+      jbo_control_step(&j->models[e], &j->datas[e], &act, j->n_sub_steps);
+      jbo_task_obs_reward(&j->models[e], &j->datas[e], j->task, obs, &rew);
+      if (j->rewards_out) j->rewards_out[(long)s * j->nenv + e] = rew;
+    }
+  }
+  return 0;
+}
+
+void jbo_rollout_heuristic(const JboModel* models, JboData* datas, int nenv, int task, int nsteps, int n_sub_steps,
+                           int nthreads, double* rewards_out) {
+  pthread_t th[256];
+  RolloutJob jobs[256];
+  int t;
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  for (t = 0; t < nthreads; t++) {
+    RolloutJob jb = {models, datas, nenv, task, nsteps, n_sub_steps, t, nthreads, 0, rewards_out, 0};
+    jobs[t] = jb;
+    if (nthreads > 1) pthread_create(&th[t], 0, heuristicWorker, &jobs[t]);
+  }
+  if (nthreads == 1) heuristicWorker(&jobs[0]);
+  else for (t = 0; t < nthreads; t++) pthread_join(th[t], 0);
+}
+
 void jbo_rollout(const JboModel* models, JboData* datas, int nenv, int task, const double* actions, int nsteps,
                  int n_sub_steps, int nthreads, double* rewards_out, double* obs_out) {
   pthread_t th[256];

@@ -95,6 +95,9 @@ int jbo_sizeof_data(void);
 /* task layer: obs/reward restated in C for the multi-threaded CPU baseline (jitterbug.py:673-763, :840-925) */
 int jbo_task_obs_reward(const JboModel* m, const JboData* d, int task, double* obs, double* reward);
 /* run `nsteps` control steps for `nenv` independent envs on `nthreads` threads; actions[nsteps][nenv] */
+double jbo_heuristic(int task, const double* obs);     /* heuristic_policies.py:6-136 on a normalised observation */
+void jbo_rollout_heuristic(const JboModel* models, JboData* datas, int nenv, int task, int nsteps, int n_sub_steps,
+                           int nthreads, double* rewards_out);   /* closed loop under that policy (evaluate_policy.py:10-35) */
 void jbo_rollout(const JboModel* models, JboData* datas, int nenv, int task, const double* actions, int nsteps,
                  int n_sub_steps, int nthreads, double* rewards_out, double* obs_out);
 #ifdef __cplusplus

@@ -127,7 +127,49 @@ def lib():
         _lib.jbo_rollout.argtypes = [C.POINTER(JboModel), C.POINTER(JboData), I, I, C.POINTER(D), I, I, I,
                                      C.POINTER(D), C.POINTER(D)]
         _lib.jbo_rollout.restype = None
+        _lib.jbo_heuristic.argtypes = [I, C.POINTER(D)]
+        _lib.jbo_heuristic.restype = D
+        _lib.jbo_rollout_heuristic.argtypes = [C.POINTER(JboModel), C.POINTER(JboData), I, I, I, I, I, C.POINTER(D)]
+        _lib.jbo_rollout_heuristic.restype = None
     return _lib
+
+
+def heuristic_c(task: int, obs) -> float:
+    """The C restatement of heuristic_policies.py used by the closed-loop rollouts (pinned by tests/test_reference_golden.py)."""
+    o = (D * 32)(*[float(x) for x in np.ravel(obs)])
+    return float(lib().jbo_heuristic(int(task), o))
+
+
+def batch_rollout(cm, task: int, qpos0, targets, n_steps: int, actions=None, n_sub_steps: int = 50, threads: int = 0):
+    """N independent episodes on the host threads.  ``qpos0[N, 16]`` initial configurations (velocities zero, like a
+    reset), ``targets[N, 4]`` = x, y, quat_w, quat_z (the simulator's target layout); ``actions[n_steps, N]`` for an
+    open-loop run, ``None`` for the closed loop under the task's heuristic policy (evaluate_policy.py:10-35).
+    Returns rewards[n_steps, N]."""
+    import os
+    L = lib()
+    n = len(qpos0)
+    models, datas = (JboModel * n)(), (JboData * n)()
+    proto = make_model(cm)
+    for e in range(n):
+        C.memmove(C.byref(models[e]), C.byref(proto), C.sizeof(JboModel))
+        b = models[e].target_body
+        models[e].body_pos[b][0], models[e].body_pos[b][1] = float(targets[e][0]), float(targets[e][1])
+        models[e].body_quat[b][0], models[e].body_quat[b][3] = float(targets[e][2]), float(targets[e][3])
+        L.jbo_reset_data(C.byref(models[e]), C.byref(datas[e]))
+        for i in range(16):
+            datas[e].qpos[i] = float(qpos0[e][i])
+        L.jbo_forward(C.byref(models[e]), C.byref(datas[e]))
+    rew = np.zeros((n_steps, n))
+    dp = C.POINTER(D)
+    threads = threads or (os.cpu_count() or 1)
+    if actions is None:
+        L.jbo_rollout_heuristic(models, datas, n, int(task), n_steps, n_sub_steps, threads, rew.ctypes.data_as(dp))
+    else:
+        a = np.ascontiguousarray(actions, dtype=np.float64)
+        assert a.shape == (n_steps, n)
+        L.jbo_rollout(models, datas, n, int(task), a.ctypes.data_as(dp), n_steps, n_sub_steps, threads,
+                      rew.ctypes.data_as(dp), None)
+    return rew
 
 
 def _np_view(struct, name):

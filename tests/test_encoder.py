@@ -117,7 +117,7 @@ def test_ensemble_and_vec_env_hook():
     ref = np.stack([O.encode_obs(o, enc_fns, k_encode=15) for o in raw])
     got = enc(torch.from_numpy(raw).cuda().contiguous()).cpu().numpy()
     assert np.abs(got - ref).max() < TOL * max(1.0, np.abs(ref).max())
-    o2, r, done = vec.step(torch.zeros(256, device="cuda"))
+    o2, r, done, _ = vec.step(torch.zeros(256, device="cuda"))
     assert o2.shape == (256, 13) and torch.isfinite(o2).all()
 
 

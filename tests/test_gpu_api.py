@@ -192,19 +192,88 @@ def test_mixed_task_batch():
 
 
 def test_vec_env_rollout_with_policy():
-    """Config 5 plumbing: auto-resetting VecEnv facade + torch MLP policy on device, episode monitor."""
+    """Config 5 plumbing: auto-resetting VecEnv facade + torch actor-critic on device, episode monitor."""
     _need_gpu()
     from jitterbug_b200 import BatchedJitterbugEnv
-    from jitterbug_b200.rollout import MLPPolicy, VecJitterbugEnv, rollout
+    from jitterbug_b200.rollout import ActorCritic, VecJitterbugEnv, rollout
     env = BatchedJitterbugEnv("move_to_pose", num_envs=512, seed=1, time_limit=0.2)     # 20-step episodes
     vec = VecJitterbugEnv(env)
     torch.manual_seed(0)
-    policy = MLPPolicy(env.obs_dim).to(env.device)
+    policy = ActorCritic(env.obs_dim).to(env.device)
     out = rollout(vec, policy, 45)
     assert vec.episode_count == 2 * 512 and out["episodes"]["count"] == 2 * 512
     assert out["steps_per_s"] > 0 and 0 <= out["mean_step_reward"] <= 1
+    assert 0 <= out["episodes"]["min"] <= out["episodes"]["mean"] <= out["episodes"]["max"] <= 20
     # after an auto-reset the env continues from a fresh episode: step counts are all 45 - 40 = 5
     assert (env.get_step_count() == 5).all()
+
+
+def test_vec_env_contract_and_rollout_buffer_equal_a_step_by_step_loop():
+    """the VecEnv contract (step_async / step_wait, dones, Monitor-style infos, first observation of the
+    next episode on done) and the on-device PPO buffer -- its contents, GAE included, must equal a plain step-by-step
+    loop over a second, identically seeded env, with and without CUDA-graph replay of the step."""
+    _need_gpu()
+    from jitterbug_b200 import BatchedJitterbugEnv
+    from jitterbug_b200.rollout import ActorCritic, RolloutBuffer, VecJitterbugEnv, collect
+    N, T, gamma, lam = 384, 24, 0.99, 0.95
+    torch.manual_seed(0)
+    policy = ActorCritic(19).to("cuda")
+
+    def make():
+        return VecJitterbugEnv(BatchedJitterbugEnv("move_to_pose", num_envs=N, seed=4, time_limit=0.1))   # 10-step episodes
+
+    # reference: explicit loop, numpy bookkeeping on the host
+    ref = make()
+    obs = ref.reset()
+    torch.manual_seed(123)
+    rows = []
+    ep_ret, ep_len = np.zeros(N), np.zeros(N, dtype=int)
+    for t in range(T):
+        o = obs.clone()
+        a, lp, v = policy.act(o)
+        ref.step_async(a)
+        obs, r, d, infos = ref.step_wait()
+        ep_ret += r.cpu().numpy(); ep_len += 1
+        dn = d.cpu().numpy()
+        il = infos.to_list()
+        for i in np.nonzero(dn)[0]:
+            assert il[i]["episode"]["l"] == ep_len[i] == 10 and il[i]["episode"]["r"] == pytest.approx(ep_ret[i], abs=1e-4)
+        assert all(il[i] == {} for i in np.nonzero(~dn)[0])
+        assert dn.all() == ((t + 1) % 10 == 0) and dn.any() == ((t + 1) % 10 == 0)
+        ep_ret[dn] = 0; ep_len[dn] = 0
+        rows.append([x.clone() for x in (o, a, lp, v, r, d)])
+        obs = obs.clone()
+    assert (ref.env.get_step_count() == T % 10).all()          # done envs were restarted: obs is a first observation
+    last_v = policy.vf(obs).squeeze(-1).detach()
+    adv = torch.zeros(N, device="cuda"); nxt = last_v
+    advs = [None] * T
+    for t in range(T - 1, -1, -1):
+        nt = (~rows[t][5]).float()
+        delta = rows[t][4] + gamma * nxt * nt - rows[t][3]
+        adv = delta + gamma * lam * nt * adv
+        advs[t] = adv.clone(); nxt = rows[t][3]
+    for use_graph in (False, True):
+        vec = make()
+        o0 = vec.reset()
+        buf = RolloutBuffer(T, N, vec.obs_dim, vec.device)
+        torch.manual_seed(123)
+        if use_graph:
+            # graph capture draws its own random numbers: compare everything that does not depend on the action noise
+            collect(vec, None, buf, o0, gamma, lam, cuda_graph=True)
+            per_step = buf.dones.sum(dim=1).cpu().numpy()
+            assert torch.isfinite(buf.obs).all() and set(per_step.tolist()) == {0, N} and (per_step == N).sum() in (2, 3)
+            assert (buf.log_probs == -np.log(2.0)).all() and ((buf.actions >= -1) & (buf.actions <= 1)).all()
+            assert vec.episode_count >= 2 * N             # warm-up and capture steps also advance the envs
+            continue
+        obs_end = collect(vec, policy, buf, o0, gamma, lam)
+        for t in range(T):
+            for got, want in zip((buf.obs[t], buf.actions[t], buf.log_probs[t], buf.values[t], buf.rewards[t], buf.dones[t]), rows[t]):
+                assert torch.equal(got, want), t
+            assert torch.allclose(buf.advantages[t], advs[t], rtol=0, atol=1e-6)
+        assert torch.equal(obs_end, obs)
+        assert torch.allclose(buf.returns, buf.advantages + buf.values)
+        lp2, v2, _ = policy.evaluate(buf.obs.reshape(T * N, -1), buf.actions.reshape(-1))
+        assert torch.allclose(lp2, buf.log_probs.reshape(-1), atol=2e-3) and torch.allclose(v2, buf.values.reshape(-1), atol=1e-5)
 
 
 def test_indexed_model_population_equals_explicit_per_env_models():

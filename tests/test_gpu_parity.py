@@ -55,7 +55,7 @@ def test_single_substep_state_parity(compiled_model, N, warm):
     a = a.cpu().numpy()
     sim = O.OracleSim(compiled_model)
     nbad_con = 0
-    worst_q = worst_v = 0.0
+    eq, ev, ev_tight = [], [], []
     skipped = 0
     for e in range(N):
         sim.set_state(qpos[e], qvel[e], warm[e], ctrl=a[e])
@@ -75,18 +75,28 @@ def test_single_substep_state_parity(compiled_model, N, warm):
         sim.step2()
         dq = np.abs(q1[e] - sim.qpos)
         dv = np.abs(v1[e] - sim.qvel)
-        worst_q = max(worst_q, float((dq / np.maximum(np.abs(sim.qpos), 1.0)).max()))
-        # velocity error relative to the scale of the velocity vector block it belongs to
-        scale = np.concatenate([np.full(3, max(1e-2, np.abs(sim.qvel[0:3]).max())),
-                                np.full(3, max(1.0, np.abs(sim.qvel[3:6]).max())),
-                                np.full(8, max(1.0, np.abs(sim.qvel[6:14]).max())),
-                                np.full(1, max(1.0, abs(sim.qvel[14])))])
-        worst_v = max(worst_v, float((dv / scale).max()))
-    print(f"single sub-step: worst scaled qpos error {worst_q:.2e}, worst scaled qvel error {worst_v:.2e}, skipped {skipped}")
-    assert skipped < N // 10
+        eq.append(float((dq / np.maximum(np.abs(sim.qpos), 1.0)).max()))
+
+        def vscale(lin_floor, ang_floor):
+            # velocity error relative to the scale of the velocity block it belongs to (linear m/s; angular, hinge and
+            # motor rad/s), floored: below the floor the comparison is absolute
+            return np.concatenate([np.full(3, max(lin_floor, np.abs(sim.qvel[0:3]).max())),
+                                   np.full(3, max(ang_floor, np.abs(sim.qvel[3:6]).max())),
+                                   np.full(8, max(ang_floor, np.abs(sim.qvel[6:14]).max())),
+                                   np.full(1, max(ang_floor, abs(sim.qvel[14])))])
+        ev.append(float((dv / vscale(1e-2, 1.0)).max()))
+        ev_tight.append(float((dv / vscale(1e-3, 0.1)).max()))
+    eq, ev, ev_tight = np.array(eq), np.array(ev), np.array(ev_tight)
+    print(f"single sub-step, {N} envs: skipped as knife-edge {skipped} ({100 * skipped / N:.2f} %); scaled qpos error max "
+          f"{eq.max():.2e} p99 {np.quantile(eq, .99):.2e}; scaled qvel error max {ev.max():.2e} p99 {np.quantile(ev, .99):.2e} "
+          f"(floors 1e-2 m/s, 1 rad/s); with floors 1e-3 m/s, 0.1 rad/s: max {ev_tight.max():.2e} p99 {np.quantile(ev_tight, .99):.2e}")
+    assert skipped <= 0.02 * N, skipped     # measured: well under 1 % of envs have a contact within 1 um of the floor
     assert nbad_con == 0, f"{nbad_con} envs with a different active contact set"
-    assert worst_q < 1e-6, worst_q          # north_star asks 1e-5 relative; measured 1.1e-7 on B200
-    assert worst_v < 1e-5, worst_v          # measured 7.5e-7
+    assert eq.max() < 1e-6, eq.max()        # north_star asks 1e-5 relative; measured 1.1e-7 on B200
+    assert ev.max() < 1e-5, ev.max()        # measured 7.5e-7
+    # a sub-step changes a velocity by h * acceleration (~0.2 rad/s for a sprung leg): with floors ten times lower the
+    # error is still bounded at the north_star figure
+    assert ev_tight.max() < 1e-5, ev_tight.max()
 
 
 def test_many_contacts_per_lane_on_device(compiled_model):
@@ -348,3 +358,149 @@ def test_per_env_kernel_single_substep_parity_including_spread_contacts(compiled
     print(f"per-env kernel: {checked} envs checked, {heavy} with a 4-contact leg, worst qpos {worst_q:.2e}, qvel {worst_v:.2e}")
     assert checked > N * 0.9 and heavy >= 10
     assert worst_q < 1e-6 and worst_v < 1e-5
+
+
+def test_mixed_batch_config3_control_step_parity(compiled_model):
+    """BASELINE.json config 3: all five tasks in one batch of 65,536 envs (task = env id mod 5, observations padded to
+    19), actions from the device heuristic-policy kernel.  After 100 free-running control steps, one more control step
+    from identical states is checked against the oracle for a stratified sample of every task: contact set at the
+    pre-step state, observation, reward, and the heuristic action itself."""
+    _need_gpu()
+    O = _oracle()
+    N, PER_TASK = 65536, 64
+    names = [TASKS[i % 5] for i in range(N)]
+    env = BatchedJitterbugEnv(names, num_envs=N, seed=5)
+    obs = env.reset()
+    for _ in range(100):
+        obs, _, _ = env.step(env.heuristic_actions(obs))
+    qpos, qvel, warm = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+    tgt = env.get_target().cpu().numpy().astype(np.float64)
+    ncon, geom, dist = [t.cpu().numpy() for t in env.contacts(32)]
+    obs_pre = obs.clone()
+    act = env.heuristic_actions(obs_pre)
+    obs1, rew1, _ = env.step(act)
+    obs_pre, act, obs1, rew1 = obs_pre.cpu().numpy(), act.cpu().numpy(), obs1.cpu().numpy(), rew1.cpu().numpy()
+    assert env.counters()["diverged_resets"] == 0
+    rng = np.random.default_rng(0)
+    sim = O.OracleSim(compiled_model)
+    for ti, task in enumerate(TASKS):
+        ids = rng.choice(np.arange(ti, N, 5), PER_TASK, replace=False)
+        tk = O.TaskOracle(sim, task)
+        D = OBS_DIM[task]
+        err_o, err_r, bad_sets, edge = [], [], 0, 0
+        for e in ids:
+            assert np.all(obs_pre[e, D:] == 0) and np.all(obs1[e, D:] == 0)         # padding
+            sim.set_state(qpos[e], qvel[e], warm[e])
+            sim.set_target(tgt[e, 0], tgt[e, 1], 2 * np.arctan2(tgt[e, 3], tgt[e, 2]))
+            sim.step1()
+            g2, d2, ex, _ = sim.contacts()
+            if any(abs(dd) < 1e-6 for dd in d2):
+                edge += 1
+            elif [int(gg) for gg, xx in zip(g2, ex) if not xx] != [int(geom[e, i]) for i in range(ncon[e])]:
+                bad_sets += 1
+            o0 = np.concatenate([np.ravel(v) for v in tk.get_observation().values()])
+            np.testing.assert_allclose(obs_pre[e, :D], o0, rtol=0, atol=4e-6)       # the state the policy saw
+            lay = env.observation_layout(task)
+            a_ref = O.heuristic(task, {k: obs_pre[e, sl].astype(np.float64) for k, sl in lay.items()})
+            assert abs(float(np.ravel(a_ref)[0]) - act[e]) < 1e-5
+            sim.control_step(act[e], 50)
+            o_ref = np.concatenate([np.ravel(v) for v in tk.get_observation().values()])
+            err_o.append(np.abs(obs1[e, :D] - o_ref).max())
+            err_r.append(abs(rew1[e] - tk.get_reward()))
+        err_o, err_r = np.array(err_o), np.array(err_r)
+        print(f"config 3, {task}: {PER_TASK} envs, obs error median {np.median(err_o):.1e} p95 {np.quantile(err_o, .95):.1e}, "
+              f"reward error p95 {np.quantile(err_r, .95):.1e}, knife-edge {edge}")
+        assert bad_sets == 0
+        assert np.median(err_o) < 2e-5, (task, np.median(err_o))
+        assert np.quantile(err_o, 0.95) < 2e-3, (task, np.quantile(err_o, 0.95))
+        assert np.quantile(err_r, 0.95) < 1e-4, (task, np.quantile(err_r, 0.95))
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_evaluate_policy_protocol_return_distributions(compiled_model, task):
+    """The reference's evaluation protocol (benchmarks/evaluate_policy.py:10-35: reset, then int(_step_limit - 1) = 999
+    control steps, reward per step) for every task under (a) its heuristic policy and (b) a uniform random policy:
+    per-episode returns of the CUDA path and of the fp64 oracle started from the same reset states must be statistically
+    indistinguishable (two-sample KS and a mean test).  Trajectories are chaotic, so nothing finer can agree."""
+    _need_gpu()
+    O = _oracle()
+    from scipy import stats
+    T, M = 999, 128
+    ti = TASKS.index(task)
+    for policy in ("heuristic", "random"):
+        env = BatchedJitterbugEnv(task, num_envs=M, seed=41 + ti)
+        obs = env.reset()
+        q0 = env.get_state()[0].cpu().numpy().astype(np.float64)
+        tgt = env.get_target().cpu().numpy().astype(np.float64)
+        g = torch.Generator(device=env.device).manual_seed(7)
+        acts = torch.rand(T, M, device=env.device, generator=g) * 2 - 1 if policy == "random" else None
+        ret = torch.zeros(M, device=env.device)
+        for k in range(T):
+            obs, r, st = env.step(acts[k] if acts is not None else env.heuristic_actions(obs))
+            ret += r
+            assert int(st.max()) == 1                                  # 999 steps never reach LAST (App. C11)
+        ret_gpu = ret.cpu().numpy().astype(np.float64)
+        rew = O.batch_rollout(compiled_model, ti, q0, tgt, T, actions=None if acts is None else acts.cpu().numpy())
+        ret_cpu = rew.sum(axis=0)
+        ks = stats.ks_2samp(ret_gpu, ret_cpu)
+        se = np.sqrt(ret_gpu.var() / M + ret_cpu.var() / M)
+        print(f"{task} / {policy}: return GPU {ret_gpu.mean():.1f} +- {ret_gpu.std():.1f}, oracle {ret_cpu.mean():.1f} +- "
+              f"{ret_cpu.std():.1f}, KS p = {ks.pvalue:.3f}")
+        assert ks.pvalue > 0.005, (task, policy, ks, ret_gpu.mean(), ret_cpu.mean())
+        assert abs(ret_gpu.mean() - ret_cpu.mean()) < 4 * se + 1e-2 * T * 1e-2, (task, policy, ret_gpu.mean(), ret_cpu.mean(), se)
+        assert env.counters()["diverged_resets"] == 0
+
+
+def test_diverged_env_restarts_with_first():
+    """mj_checkPos / mj_checkVel: a state that blows up (here a NaN planted through set_state) restarts the env; the
+    caller sees the boundary as step type FIRST with reward 0 and a fresh episode's observation."""
+    _need_gpu()
+    from jitterbug_b200.rollout import VecJitterbugEnv
+    N = 64
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=2)
+    env.reset()
+    a = torch.zeros(N, device=env.device)
+    for _ in range(3):
+        env.step(a)
+    qpos, qvel, warm = env.get_state()
+    qvel[5, 2] = float("nan")
+    qpos[9, 0] = 1e12
+    env.set_state(qpos, qvel, warm)
+    obs, rew, st = env.step(a)
+    st = st.cpu().numpy()
+    assert st[5] == 0 and st[9] == 0 and (np.delete(st, [5, 9]) == 1).all()
+    assert float(rew[5]) == 0.0 and float(rew[9]) == 0.0
+    assert torch.isfinite(obs).all()
+    assert env.counters()["diverged_resets"] == 2
+    assert env.get_step_count().cpu().numpy()[[5, 9]].tolist() == [0, 0]
+    q2 = env.get_state()[0].cpu().numpy()
+    np.testing.assert_allclose(q2[[5, 9], :3], [[0, 0, 0.035]] * 2, atol=1e-6)     # reset pose
+    obs, rew, st = env.step(a)
+    assert (st == 1).all()
+    # the VecEnv facade reports the boundary as `done`
+    vec = VecJitterbugEnv(BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=2))
+    vec.reset()
+    vec.step(a)
+    qpos, qvel, warm = vec.env.get_state()
+    qvel[7, 0] = float("nan")
+    vec.env.set_state(qpos, qvel, warm)
+    _, _, done, _ = vec.step(a)
+    assert bool(done[7]) and int(done.sum()) == 1
+
+
+def test_two_simulators_on_two_devices():
+    """Every C-ABI entry point makes its simulator's device current: two envs on two GPUs in one process."""
+    _need_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    e0 = BatchedJitterbugEnv("move_from_origin", num_envs=256, seed=1, device="cuda:0")
+    e1 = BatchedJitterbugEnv("move_from_origin", num_envs=256, seed=1, device="cuda:1")
+    torch.cuda.set_device(0)
+    e0.reset(); e1.reset()
+    for k in range(5):
+        a = torch.full((256,), 0.1 * k)
+        o0, r0, _ = e0.step(a.to("cuda:0"))
+        o1, r1, _ = e1.step(a.to("cuda:1"))
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(o0.cpu(), o1.cpu()) and torch.equal(r0.cpu(), r1.cpu())
+    assert e0.counters() == e1.counters()

@@ -99,3 +99,30 @@ def test_flatten_model_structure(compiled_model):
     # contact reference: K = 1/(dmax^2 tc^2), B = 2/(dmax tc) with tc = .02, dmax = .95
     assert flat["solref_K"] == pytest.approx(1 / (0.95 ** 2 * 0.02 ** 2))
     assert flat["solref_B"] == pytest.approx(2 / (0.95 * 0.02))
+
+
+def test_local_export_round_trip(compiled_model):
+    """mjcf.to_local_xml: the packaged local-coordinate asset is the export of the compiled model, and compiling the
+    export again gives the same model (frames composed the other way round) and the same oracle dynamics."""
+    import os
+    from oracle import oracle as O
+    cm = compiled_model
+    xml = mjcf.to_local_xml(cm)
+    asset = os.path.join(os.path.dirname(mjcf.DEFAULT_XML), "jitterbug_local.xml")
+    assert open(asset).read() == xml
+    assert 'coordinate="global"' not in xml and "fromto" not in xml
+    cm2 = mjcf.compile_xml(xml)
+    for f in ("body_mass", "body_pos", "body_ipos", "geom_pos", "geom_size", "jnt_pos", "jnt_axis", "qpos0", "dof_damping",
+              "jnt_stiffness", "actuator_gear", "actuator_biasprm", "geom_mass"):
+        np.testing.assert_allclose(np.asarray(getattr(cm2, f)), np.asarray(getattr(cm, f)), rtol=0, atol=1e-15, err_msg=f)
+    np.testing.assert_allclose(cm2.geom_density[1:], cm.geom_density[1:], rtol=0, atol=0)      # [0] is the massless floor
+    np.testing.assert_allclose(np.abs(cm2.body_quat), np.abs(cm.body_quat), atol=1e-15)
+    np.testing.assert_allclose(cm2.body_invweight0, cm.body_invweight0, rtol=1e-10)
+    np.testing.assert_allclose(cm2.dof_invweight0, cm.dof_invweight0, rtol=1e-10)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "substeps.npz"))
+    sim = O.OracleSim(cm2)
+    for i in range(0, len(g["ctrl"]), 5):
+        sim.set_state(g["qpos"][i], g["qvel"][i], g["warm"][i], ctrl=g["ctrl"][i])
+        sim.step1(); sim.step2()
+        np.testing.assert_allclose(sim.qpos, g["sub_qpos"][i], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(sim.qvel, g["sub_qvel"][i], rtol=1e-9, atol=1e-9)
