@@ -10,8 +10,11 @@ actions in [-1, 1], E envs per GPU (weak scaling), synthetic data (Philox reset 
 actions).  E defaults to 1,048,576 so the per-step state traffic (~400 MB) is larger than the 126 MB L2.
 
 Prints ONE JSON line (see the task contract): value = device-resident throughput, e2e = through the host-buffer
-C-ABI call (numpy in, numpy out, copies timed), roofline (HBM line, required schema) + fp32 (the real bound of this
-compute-bound kernel), cpu_baseline (oracle port on the host cores, bounded sample), clocks, gpu_launches.
+C-ABI call (numpy in, numpy out, copies timed), roofline = the BINDING line of this compute-bound kernel (FP32 issue
+rate: algorithmic flops of the quad sub-step, profiles/flop_model.json, against an FFMA-chain peak measured in the same
+run) with the HBM line beside it in `hbm`, cpu_baseline (oracle port on the host cores, bounded sample), clocks,
+gpu_launches, and short legs of BASELINE.json's other configs (3: mixed tasks, 4: per-env augmented models, 5: PPO
+collection with an on-device policy) under config.other_workloads.
 """
 
 from __future__ import annotations
@@ -46,13 +49,17 @@ def _flop_model():
         return {"per_substep": 7376.0, "per_newton_iteration": 1948.0, "per_contact_substep": 1272.0}
 
 
-def _traffic_per_env():
-    """DRAM bytes per env per launch from the committed ncu --set full capture (profiles/r01_v8_ncu_summary.json)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_v8_ncu_summary.json")) as f:
-            return float(json.load(f)["dram_traffic_bytes_per_env"])
-    except Exception:
-        return None
+def _traffic_per_env_step():
+    """DRAM bytes per env per CONTROL STEP (dram__bytes_read + write of one ncu --set full capture of a step-kernel
+    launch, times the launches per control step): profiles/r02_step_ncu_summary.json, else round 1's capture."""
+    for name in ("r02_step_ncu_summary.json", "r01_v8_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            return float(d.get("dram_traffic_bytes_per_env_per_control_step", d.get("dram_traffic_bytes_per_env")))
+        except Exception:
+            continue
+    return None
 
 
 def _measured_peaks():
@@ -187,39 +194,10 @@ def run_cuda(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E = args.envs
-    extra = {}
-    if args.workload == "augmented":
-        # BASELINE.json config 4: per-env randomised model parameters (legs + mass, the reference training script's
-        # defaults, benchmark.py:129-136).  --models 0 (default): every env gets its own model, drawn and compiled on
-        # the device (Philox keyed by global env id).  --models K: a population of K models compiled on the host and
-        # assigned by global env id.  Either way each env's model is staged in shared memory by the kernel.
-        from jitterbug_b200 import augmented_jitterbug
-        if args.models > 0:
-            pop = augmented_jitterbug.make_models(args.models, seed=args.seed)
-            extra = dict(models=pop, model_index=(np.arange(E, dtype=np.int64) + rank * E) % args.models)
-        else:
-            t_c = time.perf_counter()
-            deltas = augmented_jitterbug.sample_deltas(E, seed=args.seed, device=dev, env_id_offset=rank * E)
-            extra = dict(packed_models=augmented_jitterbug.compile_models_device(deltas))
-            torch.cuda.synchronize(dev)
-            compile_s = time.perf_counter() - t_c
-            del deltas
-    task = TASK
-    if args.workload == "mixed":
-        # BASELINE.json config 3: all five tasks in one batch (task = global env id mod 5, observations padded to 19),
-        # actions from the device port of the reference's heuristic policies (one extra kernel launch per step)
-        from jitterbug_b200.batched_env import TASKS
-        task = [TASKS[(rank * E + e) % 5] for e in range(E)]
-    env = BatchedJitterbugEnv(task, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    n_act = 4
-    acts = [torch.rand(E, device=dev, generator=g) * 2 - 1 for _ in range(n_act)]
-    env.reset()
-    stream = torch.cuda.current_stream(dev)
-    mixed = args.workload == "mixed"
-
-    def action(i):
-        return env.heuristic_actions() if mixed else acts[i % n_act]
+    hbm_peak, which = _measured_peaks()
+    fm = _flop_model()
+    fp32_peak = C.c_double()
+    _native.check(_native.load().jb_measure_fp32_peak(local, C.byref(fp32_peak)))
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -227,31 +205,83 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def allmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def make_env(workload, E):
+        """(env, action source, description) of one of BASELINE.json's batched configurations on this rank."""
+        extra, note = {}, ""
+        task = TASK
+        if workload == "augmented":
+            # config 4: per-env randomised model parameters (legs + mass, the reference training script's defaults,
+            # benchmark.py:129-136).  --models 0 (default): every env gets its own model, drawn and compiled on the
+            # device (Philox keyed by global env id); --models K: a host-compiled population of K models assigned by
+            # global env id.  Either way each env's model is staged in shared memory by the kernel.
+            from jitterbug_b200 import augmented_jitterbug
+            if args.models > 0:
+                pop = augmented_jitterbug.make_models(args.models, seed=args.seed)
+                extra = dict(models=pop, model_index=(np.arange(E, dtype=np.int64) + rank * E) % args.models)
+                note = f", per-env augmented models (population {args.models}, host-compiled)"
+            else:
+                t_c = time.perf_counter()
+                deltas = augmented_jitterbug.sample_deltas(E, seed=args.seed, device=dev, env_id_offset=rank * E)
+                extra = dict(packed_models=augmented_jitterbug.compile_models_device(deltas))
+                torch.cuda.synchronize(dev)
+                note = f", one augmented model per env compiled on the device ({time.perf_counter() - t_c:.2f} s)"
+                del deltas
+        elif workload == "mixed":
+            # config 3: all five tasks in one batch (task = global env id mod 5, observations padded to 19), actions from
+            # the device port of the reference's heuristic policies (one extra kernel launch per step)
+            from jitterbug_b200.batched_env import TASKS
+            task = [TASKS[(rank * E + e) % 5] for e in range(E)]
+        env = BatchedJitterbugEnv(task, num_envs=E, device=dev, seed=args.seed, env_id_offset=rank * E, **extra)
+        g = torch.Generator(device=dev).manual_seed(1234 + rank)
+        acts = [torch.rand(E, device=dev, generator=g) * 2 - 1 for _ in range(4)]
+        env.reset()
+        action = (lambda i: env.heuristic_actions()) if workload == "mixed" else (lambda i: acts[i % 4])
+        what = ("all five tasks (env id mod 5), device heuristic policies" if workload == "mixed" else
+                f"{TASK}, uniform random actions") + note
+        return env, acts, action, what
+
+    def measure(env, action, burn_in, warmup, steps, sample_clocks=False):
+        """Device-timed steady-state throughput of `steps` control steps (max over ranks) + per-step kernel times."""
+        stream = torch.cuda.current_stream(dev)
+        for i in range(burn_in):
+            env.step(action(i))
+        for i in range(warmup):
+            env.step(action(i))
+        barrier()
+        c0, l0 = env.counters(), env.launch_count()
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        ev[0].record(stream)
+        for i in range(steps):
+            env.step(action(i))
+            ev[i + 1].record(stream)
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        total_ms = allmax(ev[0].elapsed_time(ev[-1]))
+        c1, l1 = env.counters(), env.launch_count()
+        sub = max(c1["substeps"] - c0["substeps"], 1)
+        newton = (c1["newton_iterations"] - c0["newton_iterations"]) / sub
+        ncon = (c1["contacts"] - c0["contacts"]) / sub
+        flops = 50 * (fm["per_substep"] + fm["per_newton_iteration"] * newton + fm["per_contact_substep"] * ncon)
+        ms_step = float(np.mean([ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]))
+        tf = flops * env.num_envs / (ms_step * 1e-3) / 1e12
+        return {"value": world * env.num_envs * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps,
+                "kernel_ms": ms_step, "newton": newton, "ncon": ncon, "flops_per_control_step": flops,
+                "fp32_tflops": tf, "fp32_frac": tf / fp32_peak.value if fp32_peak.value else None,
+                "launches_per_step": (l1 - l0) / steps, "clocks": clocks}
+
+    env, acts, action, what = make_env(args.workload, E)
+    mixed = args.workload == "mixed"
     # untimed burn-in to the stationary regime (motor spun up, contacts active: BASELINE.md section 4 asks for
-    # ~200 control steps before sampling), then the W warm-up steps of the contract
-    for i in range(args.burn_in):
-        env.step(action(i))
-    for i in range(args.warmup):
-        env.step(action(i))
-    barrier()
-    c0 = env.counters()
-    sampler = ClockSampler(local) if rank == 0 else None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    ev[0].record(stream)
-    for i in range(args.steps):
-        env.step(action(i))
-        ev[i + 1].record(stream)
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    c1 = env.counters()
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * E * args.steps / (total_ms_max * 1e-3)
+    # ~200 control steps before sampling), then the W warm-up steps of the contract, then exactly K timed steps
+    m = measure(env, action, args.burn_in, args.warmup, args.steps, sample_clocks=True)
 
     # ---- e2e: host buffers through the C-ABI host entry point (H2D actions, D2H obs/reward/step_type each step)
     h_pin = [a.cpu().pin_memory() for a in acts]            # inputs in pinned host memory (kept alive by h_pin)
@@ -261,13 +291,9 @@ def run_cuda(args):
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        env.step_host(h_acts[i % n_act])
+        env.step_host(h_acts[i % 4])
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * e2e_steps / float(t.item())
+    e2e_value = world * E * e2e_steps / allmax(time.perf_counter() - t0)
 
     # ---- optional end-of-rollout statistics gather (the only collective; NOT in the step path)
     stats = torch.stack([env._reward.double().sum(), (env._reward.double() ** 2).sum(),
@@ -275,57 +301,95 @@ def run_cuda(args):
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     mean_reward = float(stats[0] / stats[2])
+    obs_dim = env.obs_dim
+    env.close()
+    del env, acts, action
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json's other batched configurations, short legs (same timing method, fewer steps)
+    other = {}
+    if not args.no_other_workloads and args.workload == "shared":
+        k_o, b_o = max(3, min(args.steps, 6)), min(args.burn_in, 80)
+        for name, wl, E_o in (("config3_mixed_tasks_heuristic_policies", "mixed", 65536),
+                              ("config4_augmented_per_env_models", "augmented", max((1 << 20) // world, 1024))):
+            env_o, _, action_o, what_o = make_env(wl, E_o)
+            mo = measure(env_o, action_o, b_o, 3, k_o)
+            other[name] = {"value": mo["value"], "unit": UNIT, "envs_per_gpu": E_o, "workload": what_o, "steps": k_o,
+                           "burn_in_steps": b_o, "ms_per_step": mo["ms_per_step"], "fp32_frac": mo["fp32_frac"],
+                           "newton_iters_per_substep": mo["newton"], "contacts_per_substep": mo["ncon"]}
+            env_o.close()
+            del env_o, action_o
+            torch.cuda.empty_cache()
+        # config 5: PPO collection (action + log-prob + value per step into an on-device buffer, GAE) on move_to_pose
+        from jitterbug_b200.rollout import ActorCritic, RolloutBuffer, VecJitterbugEnv, collect
+        E_r, horizon = 262144, 16
+        vec = VecJitterbugEnv(BatchedJitterbugEnv("move_to_pose", num_envs=E_r, device=dev, seed=args.seed,
+                                                  env_id_offset=rank * E_r))
+        torch.manual_seed(rank)
+        policy = ActorCritic(vec.obs_dim).to(dev)
+        buf = RolloutBuffer(horizon, E_r, vec.obs_dim, dev)
+        o = vec.reset()
+        for i in range(b_o):
+            o, _, _, _ = vec.step(torch.rand(E_r, device=dev) * 2 - 1)
+        cache = {}
+        o = collect(vec, policy, buf, o.clone(), cuda_graph=True, _graph_cache=cache)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = collect(vec, policy, buf, o, cuda_graph=True, _graph_cache=cache)
+        e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+        other["config5_ppo_collection_move_to_pose"] = {
+            "value": world * E_r * horizon / (ms * 1e-3), "unit": "env+policy control_steps/s", "envs_per_gpu": E_r,
+            "workload": "move_to_pose, ActorCritic 350-250 on device, action + log-prob + value per step into the on-device "
+                        "buffer, GAE at the end of the horizon, CUDA-graph replay of policy + env step",
+            "horizon": horizon, "burn_in_steps": b_o}
+        vec.close()
+        del vec, buf, policy, cache
+        torch.cuda.empty_cache()
 
     if rank == 0:
-        sub = c1["substeps"] - c0["substeps"]
-        newton = (c1["newton_iterations"] - c0["newton_iterations"]) / max(sub, 1)
-        ncon = (c1["contacts"] - c0["contacts"]) / max(sub, 1)
-        fm = _flop_model()
-        flops_per_step = 50 * (fm["per_substep"] + fm["per_newton_iteration"] * newton + fm["per_contact_substep"] * ncon)
-        ms_kernel = float(np.mean(kernel_ms))
-        hbm_peak, which = _measured_peaks()
+        ms_kernel = m["kernel_ms"]
         achieved_gbs = BYTES_PER_ENV_STEP * E / (ms_kernel * 1e-3) / 1e9
-        fp32_peak = C.c_double()
-        _native.check(_native.load().jb_measure_fp32_peak(local, C.byref(fp32_peak)))
-        achieved_tf = flops_per_step * E / (ms_kernel * 1e-3) / 1e12
+        traffic = _traffic_per_env_step()
         # CPU baseline: bounded sample of the same workload on the host cores (oracle port)
         cores = os.cpu_count() or 1
         cpu = None
-        if world >= 1 and not args.no_cpu_baseline:
+        if not args.no_cpu_baseline:
             n_env, n_steps = 16 * cores, 1000          # one full 1000-step episode per env, ~5-20 s of CPU work
             rate, dt, _ = cpu_rollout_rate(n_env, n_steps, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{n_env} envs x {n_steps} control steps ({dt:.1f} s), fp64 C oracle port, {cores} pthreads"}
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("all five tasks (env id mod 5), device heuristic policies" if mixed else
-                                    f"{TASK}, uniform random actions") + f", {E} envs per GPU x {world} GPU, 50 sub-steps + "
-                                   f"reward + obs per step, episodes of 1000 steps with in-kernel auto-reset"
-                                   + ((f", per-env augmented models (population {args.models}, host-compiled)"
-                                       if args.models > 0 else
-                                       f", one augmented model per env compiled on the device ({compile_s:.2f} s)")
-                                      if args.workload == "augmented" else ""),
+            "config": {"workload": what + f", {E} envs per GPU x {world} GPU, 50 sub-steps + reward + obs per step, "
+                                   f"episodes of 1000 steps with in-kernel auto-reset",
                        "envs_per_gpu": E, "task": "mixed" if mixed else TASK, "l2_policy": "inputs larger than L2 "
-                       f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per step vs 126 MB L2)"
+                       f"({BYTES_PER_ENV_STEP * E / 1e6:.0f} MB state traffic per launch vs 126 MB L2)"
                        if BYTES_PER_ENV_STEP * E > 126e6 else "inputs smaller than L2 (compute-bound kernel)",
                        "parallelism": f"env-sharded x{world}, no collective in the step path",
                        "burn_in_steps": args.burn_in,
-                       "newton_iters_per_substep": newton, "contacts_per_substep": ncon,
-                       "mean_reward": mean_reward},
+                       "launches_per_control_step": m["launches_per_step"],
+                       "newton_iters_per_substep": m["newton"], "contacts_per_substep": m["ncon"],
+                       "mean_reward": mean_reward, "other_workloads": other},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 4 * E,
-                    "d2h_bytes_per_step": 4 * E * (env.obs_dim + 2), "steps": e2e_steps},
-            "gpu_launches": args.steps * (2 if mixed else 1),
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak,
-                         "traffic": (_traffic_per_env() * E if _traffic_per_env() else None), "peak_source": which,
-                         "note": "kernel is FP32-issue bound by design (50 sub-steps fused on chip); see fp32"},
-            "fp32": {"achieved": achieved_tf, "peak": fp32_peak.value, "unit": "TFLOP/s",
-                     "frac": achieved_tf / fp32_peak.value if fp32_peak.value else None,
-                     "flops_per_control_step": flops_per_step, "peak_source": "FFMA-chain microbenchmark, this run"},
+                    "d2h_bytes_per_step": 4 * E * (obs_dim + 2), "steps": e2e_steps},
+            "gpu_launches": int(round(args.steps * m["launches_per_step"])),
+            "roofline": {"bound": "fp32", "achieved": m["fp32_tflops"], "peak": fp32_peak.value, "unit": "TFLOP/s",
+                         "frac": m["fp32_frac"], "traffic": (traffic * E if traffic else None),
+                         "flops_per_control_step": m["flops_per_control_step"],
+                         "peak_source": "FFMA-chain microbenchmark in this run (MEASURED_PEAKS.json carries no FP32 number)",
+                         "note": "compute-bound by design (50 sub-steps fused on chip): the binding roofline is the FP32 issue "
+                                 "rate; achieved = algorithmic flops of the quad sub-step (profiles/flop_model.json) x envs / "
+                                 "device time of the control step's step-kernel launches; traffic = DRAM bytes per control "
+                                 "step from the ncu capture in profiles/"},
+            "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                    "peak_source": which, "bytes_per_env_step": BYTES_PER_ENV_STEP},
             "kernel_ms": ms_kernel,
-            "clocks": clocks,
+            "clocks": m["clocks"],
         }
         if cpu:
             out["cpu_baseline"] = cpu
@@ -358,6 +422,7 @@ def main():
                     help="augmented: 0 = one device-compiled model per env; K > 0 = host-compiled population of K")
     ap.add_argument("--burn-in", type=int, default=150, help="untimed control steps before warm-up (steady state)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-workloads", action="store_true", help="skip the short config 3 / 4 / 5 legs")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything else that lands on file descriptor 1 (NCCL's version banner, any
     # library chatter) is sent to stderr, and the line itself goes to the saved descriptor

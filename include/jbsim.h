@@ -106,8 +106,18 @@ int jb_sim_get_slot_order(JbSim* sim, int32_t* perm_dev, void* stream);
 int jb_sim_get_load(JbSim* sim, int32_t* load_dev, void* stream);
 
 /* counters since creation: [0] physics sub-steps, [1] Newton iterations, [2] active contacts summed over sub-steps,
- * [3] contact-slot overflows, [4] diverged-state resets.  Synchronises the device. */
+ * [3] contact-slot overflows (always 0: a lane has a slot for every contact its geoms can produce), [4] diverged-state
+ * resets.  Synchronises the device. */
 int jb_sim_get_counters(JbSim* sim, unsigned long long* out5_host);
+
+/* Self-clearance monitor.  MuJoCo would also test the geom pairs of non-adjacent bodies (leg - leg, leg - rotor, lower leg -
+ * core; reference model jitterbug.xml); the step kernel generates only floor contacts, on the
+ * argument that those pairs never touch.  The monitor measures it: a conservative lower bound (cylinders as capsules,
+ * boxes / ellipsoids as bounding spheres) of the smallest distance over all such pairs, per env, at the current state.
+ * jb_sim_step runs it every 8th control step into running counters.  clearance_dev[num_envs] (optional): evaluate now
+ * and write the per-env bound in metres.  out3_host (optional; synchronises): env-states checked so far, how many of
+ * them had a bound below zero, and the smallest bound seen, in metres. */
+int jb_sim_self_clearance(JbSim* sim, float* clearance_dev, double* out3_host, void* stream);
 
 /* Profiling builds only (-DJBQ_PHASE_TIMERS): clock64 cycles summed over warps for the 7 phases of the sub-step
  * ([1] leg kinematics+collision, [2] root/rotor, [3] extra geoms, [4] factor M + smooth solve, [5] warm-start
@@ -182,6 +192,9 @@ int jb_encode_obs(const JbEncoderDesc* desc, const float* params_dev, const floa
                   int n, int obs_stride, float* out_dev, int out_stride, uint64_t seed, uint64_t counter, void* stream);
 
 int jb_sim_num_envs(const JbSim* sim);
+/* kernels of this library launched so far on behalf of `sim` by jb_sim_step / _reset / _get_contacts (step kernel
+ * segments and the three slot-order sort kernels after each), jb_sim_observe and jb_sim_heuristic_actions */
+unsigned long long jb_sim_launch_count(const JbSim* sim);
 int jb_sim_obs_stride(const JbSim* sim);
 const char* jb_last_error(void);
 const char* jb_version(void);

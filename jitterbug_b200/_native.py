@@ -64,6 +64,7 @@ SYMBOLS = {
     "jb_sim_set_slot_order": (C.c_int, [_P, C.c_int, _P, _P]),
     "jb_sim_get_slot_order": (C.c_int, [_P, _P, _P]),
     "jb_sim_get_load": (C.c_int, [_P, _P, _P]),
+    "jb_sim_self_clearance": (C.c_int, [_P, _P, C.POINTER(C.c_double), _P]),
     "jb_sim_get_counters": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "jb_sim_get_phase_cycles": (C.c_int, [_P, C.POINTER(C.c_ulonglong)]),
     "jb_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
@@ -75,6 +76,7 @@ SYMBOLS = {
     "jb_encode_obs": (C.c_int, [C.POINTER(JbEncoderDesc), _P, _P, _P, C.c_int, C.c_int, _P, C.c_int, C.c_uint64,
                                 C.c_uint64, _P]),
     "jb_sim_num_envs": (C.c_int, [_P]),
+    "jb_sim_launch_count": (C.c_ulonglong, [_P]),
     "jb_sim_obs_stride": (C.c_int, [_P]),
     "jb_last_error": (C.c_char_p, []),
     "jb_version": (C.c_char_p, []),

@@ -298,6 +298,23 @@ class BatchedJitterbugEnv:
         _native.check(self._lib.jb_sim_get_load(self._h, C.c_void_p(ld.data_ptr()), self._stream()))
         return ld
 
+    def self_clearance(self, per_env: bool = False):
+        """Self-collision monitor (see include/jbsim.h): dict with the env-states checked so far, how many had a
+        conservative clearance bound below zero and the smallest bound seen (metres); with ``per_env=True`` the monitor
+        is also evaluated now and the per-env bounds [N] are returned under ``"clearance"``."""
+        out = (C.c_double * 3)()
+        cl = torch.empty(self.num_envs, device=self.device, dtype=torch.float32) if per_env else None
+        _native.check(self._lib.jb_sim_self_clearance(self._h, C.c_void_p(cl.data_ptr()) if per_env else None, out,
+                                                      self._stream()))
+        res = {"checked": int(out[0]), "below_zero": int(out[1]), "min_clearance_m": float(out[2])}
+        if per_env:
+            res["clearance"] = cl
+        return res
+
+    def launch_count(self) -> int:
+        """Kernels of libjbsim launched so far for this env (step segments, slot-order sorts, task kernels)."""
+        return int(self._lib.jb_sim_launch_count(self._h))
+
     def counters(self):
         """dict of device counters since creation (synchronises)."""
         out = (C.c_ulonglong * 5)()

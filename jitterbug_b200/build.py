@@ -1,6 +1,6 @@
 """Builds ``jitterbug_b200/_lib/libjbsim.so`` (CUDA, sm_100a) in-tree with nvcc.
 
-Six objects: the fused quad-per-env step kernel in its two instantiations (shared model / per-env models), the C-ABI +
+Seven objects: the fused quad-per-env step kernel in its two instantiations (shared model / per-env models), the C-ABI +
 utility kernels, the observation encoder and the on-device model compiler; they compile in parallel.  ``python -m jitterbug_b200.build`` or ``build()``.
 """
 
@@ -18,7 +18,7 @@ LIBDIR = os.path.join(_HERE, "_lib")
 LIB = os.path.join(LIBDIR, "libjbsim.so")
 # (source, object stem, extra flags): the step kernel is instantiated twice, see the head of jb_sim_kernel.cu
 UNITS = [("jb_sim_kernel.cu", "jb_sim_kernel", []), ("jb_sim_kernel.cu", "jb_sim_kernel_perenv", ["-DJB_PER_ENV_BUILD"]),
-         ("jb_api.cu", "jb_api", []), ("jb_sort.cu", "jb_sort", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
+         ("jb_api.cu", "jb_api", []), ("jb_sort.cu", "jb_sort", []), ("jb_monitor.cu", "jb_monitor", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
 # -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
 # 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -76,5 +76,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, extra_flags, units=("jb_sim_kernel",)) -> str:
+    """Tuning helper: ``_lib/variants/<name>/libjbsim.so`` with ``extra_flags`` (e.g. ``-DJB_PHASE_SYNC=0x52``) applied to
+    the listed object stems (default: the shared-model step kernel); select it at run time with ``JB_LIB=<path>``."""
+    build()
+    vdir = os.path.join(LIBDIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    for unit, stem, extra in UNITS:
+        if stem in units:
+            obj = os.path.join(vdir, stem + ".o")
+            r = subprocess.run([nvcc] + NVCC_FLAGS + extra + list(extra_flags) + ["-c", os.path.join(CSRC, unit), "-o", obj],
+                               capture_output=True, text=True)
+            with open(os.path.join(vdir, stem + ".ptxas.log"), "w") as f:
+                f.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {unit}:\n{r.stdout}\n{r.stderr}")
+        else:
+            obj = os.path.join(LIBDIR, stem + ".o")
+        objs.append(obj)
+    lib = os.path.join(vdir, "libjbsim.so")
+    r = subprocess.run([nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":      # python -m jitterbug_b200.build --variant NAME -DFOO=1 ...
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

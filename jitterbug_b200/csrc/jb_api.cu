@@ -46,17 +46,18 @@ struct JbSim {
   // launch re-sorts for the next one
   int* perm_buf; int* sort_scratch; int perm_cur; int auto_sort;
   int seg_sub;                      // sub-steps per launch of a control step when the slot order is being sorted
+  unsigned long long launches;      // kernels of this library launched for this simulator (step path + utilities)
+  unsigned long long steps;         // control steps taken (the self-clearance monitor runs every JB_MONITOR_PERIOD-th)
+  int monitor;                      // self-clearance monitor on / off
 };
 
 static cudaError_t launch(JbSim* s, const JbLaunchArgs& a, cudaStream_t st) {
   static int force256 = -1;                  // tuning: JBSIM_KERNEL=256 runs the shared model through the 256-thread build
   if (force256 < 0) { const char* e = getenv("JBSIM_KERNEL"); force256 = (e && atoi(e) == 256) ? 1 : 0; }
+  s->launches++;
   return (s->per_env || force256) ? jb_launch_sim_perenv(s->d, a, st) : jb_launch_sim(s->d, a, st);
 }
 
-#ifndef JBQ_CAP
-#define JBQ_CAP 8
-#endif
 #define JB_REP (4 * JBQ_CAP)   /* 4 lanes x JBQ_CAP staging slots per env (same macro as jb_quad.cuh) */
 
 // staging [N][32] (-1 = empty) -> compact lists in ascending MuJoCo geom id
@@ -191,6 +192,7 @@ extern "C" {
 const char* jb_last_error(void) { return g_err.c_str(); }
 const char* jb_version(void) { return "jbsim 0.2 (sm_100a, quad-per-env)"; }
 int jb_sim_num_envs(const JbSim* sim) { return sim ? sim->cfg.num_envs : 0; }
+unsigned long long jb_sim_launch_count(const JbSim* sim) { return sim ? sim->launches : 0; }
 int jb_sim_obs_stride(const JbSim* sim) { return sim ? sim->cfg.obs_stride : 0; }
 
 static int grid_of(int n) { return (n + JB_BLOCK - 1) / JB_BLOCK; }
@@ -228,6 +230,12 @@ static int sim_fill(JbSim* s, const JbSimConfig* cfg, const int32_t* task_ids_ho
   CUDA_TRY(cudaMemset(d.episode, 0, N * sizeof(int)));
   CUDA_TRY(cudaMemset(d.reset_next, 1, N));           // a step() before any reset() is a reset (dm_control)
   CUDA_TRY(cudaMemset(d.counters, 0, 16 * sizeof(unsigned long long)));
+  {
+    const long long big = 0x7fffffffffffffffLL;                        // counters[7]: running minimum
+    CUDA_TRY(cudaMemcpy(d.counters + 7, &big, sizeof(big), cudaMemcpyHostToDevice));
+  }
+  s->monitor = 1;
+  if (const char* e = getenv("JBSIM_MONITOR")) s->monitor = atoi(e) != 0;
   if (task_ids_host) CUDA_TRY(cudaMemcpy(d.task, task_ids_host, N * sizeof(int), cudaMemcpyHostToDevice));
   else CUDA_TRY(cudaMemset(d.task, 0, N * sizeof(int)));
   CUDA_TRY(jb_configure_kernels_perenv());
@@ -363,12 +371,17 @@ int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* rewar
     CUDA_TRY(launch(s, a, st));
     if (s->auto_sort) {
       CUDA_TRY(jb_sort_by_load(s->d.load, s->d.N, a.sub_count, s->perm_buf + (size_t)(cur ^ 1) * N, s->sort_scratch, st));
+      s->launches += 3;
       cur ^= 1;
     }
   }
   if (s->auto_sort) {
     if (cur == 1) CUDA_TRY(cudaMemcpyAsync(s->perm_buf, s->perm_buf + N, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
     s->d.perm = s->perm_buf;
+  }
+  if (s->monitor && (s->steps++ % JB_MONITOR_PERIOD) == 0) {
+    CUDA_TRY(jb_launch_self_clearance(s->d, nullptr, st));
+    s->launches++;
   }
   return 0;
 }
@@ -423,6 +436,7 @@ int jb_sim_step_host(JbSim* s, const float* actions_host, float* obs_host, float
 int jb_sim_observe(JbSim* s, float* obs_dev, float* reward_dev, void* stream) {
   if (!s || (!obs_dev && !reward_dev)) return fail("jb_sim_observe: null argument");
   JB_GUARD(s);
+  s->launches++;
   jb_observe_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, obs_dev, reward_dev);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -431,6 +445,7 @@ int jb_sim_observe(JbSim* s, float* obs_dev, float* reward_dev, void* stream) {
 int jb_sim_heuristic_actions(JbSim* s, const float* obs_dev, float* actions_dev, void* stream) {
   if (!s || !obs_dev || !actions_dev) return fail("jb_sim_heuristic_actions: null argument");
   JB_GUARD(s);
+  s->launches++;
   jb_heuristic_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(s->d, obs_dev, actions_dev);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -543,6 +558,25 @@ int jb_sim_get_slot_order(JbSim* s, int32_t* perm_dev, void* stream) {
   } else {
     jb_iota_kernel<<<grid_of(s->d.N), JB_BLOCK, 0, (cudaStream_t)stream>>>(perm_dev, s->d.N);
     CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+int jb_sim_self_clearance(JbSim* s, float* clearance_dev, double* out3_host, void* stream) {
+  if (!s) return fail("jb_sim_self_clearance: null sim");
+  JB_GUARD(s);
+  if (clearance_dev) {
+    CUDA_TRY(jb_launch_self_clearance(s->d, clearance_dev, (cudaStream_t)stream));
+    s->launches++;
+  }
+  if (out3_host) {
+    unsigned long long c[3];
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(c, s->d.counters + 5, sizeof(c), cudaMemcpyDeviceToHost));
+    out3_host[0] = (double)c[0];
+    out3_host[1] = (double)c[1];
+    out3_host[2] = c[0] ? (double)(long long)c[2] * 1e-9 : 0.0;
   }
   return 0;
 }

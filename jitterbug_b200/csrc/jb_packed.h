@@ -100,4 +100,12 @@ JBP_HD static inline void jb_pack_model(const MODEL& m, REAL* p) {
   }
 }
 #endif
+/* contact slots per lane of the quad kernel (jb_quad.cuh); also sizes the contact-report staging of the C-ABI */
+#ifndef JBQ_CAP
+#define JBQ_CAP 15                      /* contact slots per lane = the most a lane can produce: its leg's foot and knee
+                                           spheres (1 + 1) and two cylinders (4 + 4), plus this lane's extra geoms (a core box:
+                                           4 corners; or a cylinder + an ellipsoid: 4 + 1), so no contact is ever dropped.
+                                           The active-row masks pack 4 bits per slot. */
+#endif
+
 #endif

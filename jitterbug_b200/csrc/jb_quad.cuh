@@ -35,9 +35,13 @@
 #ifdef JBQ_DEBUG_COUNT
 static long long g_jbq_ls_iters = 0, g_jbq_newton_trips = 0, g_jbq_spread_moves = 0;
 #endif
-#ifndef JBQ_CAP
-#define JBQ_CAP 8                       /* contact slots per lane (own leg's geoms + this lane's extra geoms); the active-row
-                                           masks pack 4 bits per slot into 32 bits, so 8 is also the most they hold */
+#if JBQ_CAP > 16
+#error "the active-row masks hold 16 slots"
+#endif
+#if JBQ_CAP > 8
+typedef uint64_t jbq_mask_t;
+#else
+typedef uint32_t jbq_mask_t;
 #endif
 // JBQ_SPREAD: balance a heavy lane's leg contacts over its quad (see the leg phase of jbq_substep).  It shortens the
 // contact loops of the fullest lane from 4 to 2 trips, but costs ~800 instructions and 15 live accumulators: a gain where
@@ -64,8 +68,9 @@ enum { JBQ_TAG_LOWER = 256, JBQ_TAG_FOREIGN = 512 };
 template <typename T> struct QCon {
   // world-frame rows of the 3 x 8 contact Jacobian over (root lin 3, root ang 3, jA, jB): u_world = J (a_root, qA, qB)
   // with (qA, qB) = (la, lb) of this lane's leg, or (motor, -) for a rotor contact.  Row k = [r_k, x cross r_k, r_k.ja,
-  // r_k.jb], r_k = world axis k in root coordinates.  Built once when the contact is created.
-  T Jx[8], Jy[8], Jz[8];
+  // r_k.jb], r_k = world axis k in root coordinates = row k of the sub-step's Rw (QFrame), which every contact shares:
+  // only the five contact-specific entries [x cross r_k (3), r_k.ja, r_k.jb] are stored.  Built once per sub-step.
+  T Jx[5], Jy[5], Jz[5];
   T D, ar0, uref[3];                    // 1/Rpy, -K*imp*dist, -B*v_point (WORLD comps)
   T ww[3], jv[3];                       // solver scratch (WORLD comps): J a - uref ; J search
   int kind;
@@ -275,10 +280,9 @@ JBQ_BUILD_ATTR void jbq_build(const T* g, QCon<T>& c, const QFrame<T>& fr, const
   for (int k = 0; k < 3; k++) {
     T* J = rows[k];
     const T* rk = fr.Rw + 3 * k;
-    J[0] = rk[0]; J[1] = rk[1]; J[2] = rk[2];
-    cross3(J + 3, x, rk);
-    J[6] = dot3(rk, ja); J[7] = dot3(rk, jb);
-    vw[k] = dot3(J, fr.vr) + dot3(J + 3, fr.w) + J[6] * b.qd1 + J[7] * b.qd2;
+    cross3(J, x, rk);
+    J[3] = dot3(rk, ja); J[4] = dot3(rk, jb);
+    vw[k] = dot3(rk, fr.vr) + dot3(J, fr.w) + J[3] * b.qd1 + J[4] * b.qd2;
   }
   T imp = jbq_impedance<T>(g + G_SOLIMP, dist);
   T mu = g[G_FRIC];
@@ -410,28 +414,27 @@ template <typename T> JB_HD void jbq_rows(T* jar, const T* ww, T mu, T ar0) {
   jar[3] = ww[2] + mu * ww[0] - ar0;
 }
 
-// out = J_c a in WORLD comps
-template <typename T> JB_HD void jbq_J_apply(T* out, const QCon<T>& c, const QVec<T>& a, T laf, T lbf) {
+// out = J_c a in WORLD comps; lin = Rw a_lin (the part every contact shares)
+template <typename T> JB_HD void jbq_J_apply(T* out, const QCon<T>& c, const T* lin, const QVec<T>& a, T laf, T lbf) {
   const T qa = c.kind == QK_ROTOR ? a.mo : ((JBQ_SPREAD && c.kind == QK_LEG_F) ? laf : a.la);
   const T qb = (JBQ_SPREAD && c.kind == QK_LEG_F) ? lbf : a.lb;
   const T* const rows[3] = {c.Jx, c.Jy, c.Jz};
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     const T* J = rows[k];
-    T s = J[6] * qa + J[7] * qb;
-#pragma unroll
-    for (int i = 0; i < 6; i++) s += J[i] * a.r[i];
-    out[k] = s;
+    out[k] = lin[k] + J[0] * a.r[3] + J[1] * a.r[4] + J[2] * a.r[5] + J[3] * qa + J[4] * qb;
   }
 }
 
 // ww = J_c a - uref (dst = 0) or jv = J_c a (dst = 1) for every contact of this lane; (laf, lbf): the leg entries of `a`
 // in the lane that owns this lane's foreign contacts
-template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a, int dst, T laf, T lbf) {
+template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QFrame<T>& fr, const QVec<T>& a, int dst, T laf, T lbf) {
+  T lin[3];
+  mulMV(lin, fr.Rw, a.r);
   for (int i = 0; i < cs.n; i++) {
     QCon<T>& c = cs.c[i];
     T u[3];
-    jbq_J_apply(u, c, a, laf, lbf);
+    jbq_J_apply(u, c, lin, a, laf, lbf);
     if (dst == 0) { c.ww[0] = u[0] - c.uref[0]; c.ww[1] = u[1] - c.uref[1]; c.ww[2] = u[2] - c.uref[2]; }
     else { c.jv[0] = u[0]; c.jv[1] = u[1]; c.jv[2] = u[2]; }
   }
@@ -440,26 +443,29 @@ template <typename T> JB_HD void jbq_apply_all(QConSet<T>& cs, const QVec<T>& a,
 // This lane's constraint forces at the current ww: partial generalized force (root 6 + motor partial in out7[6], leg in
 // *fla / *flb) and the active-row mask (4 bits per contact).
 template <typename T>
-JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, T* ffa, T* ffb) {
-  uint32_t mask = 0;
+JB_HD jbq_mask_t jbq_forces(const QConSet<T>& cs, const QFrame<T>& fr, T mu, T* out7, T* fla, T* flb, T* ffa, T* ffb) {
+  jbq_mask_t mask = 0;
 #pragma unroll
   for (int i = 0; i < 7; i++) out7[i] = 0;
   *fla = 0; *flb = 0; *ffa = 0; *ffb = 0;
+  T fsum[3] = {0, 0, 0};            // sum of the contact forces in WORLD comps: the linear root force is Rw' fsum
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
     T jar[4];
     jbq_rows(jar, c.ww, mu, c.ar0);
-    mask |= ((jar[0] < (T)0 ? 1u : 0u) | (jar[1] < (T)0 ? 2u : 0u) | (jar[2] < (T)0 ? 4u : 0u) | (jar[3] < (T)0 ? 8u : 0u)) << (4 * i);
+    mask |= (jbq_mask_t)((jar[0] < (T)0 ? 1u : 0u) | (jar[1] < (T)0 ? 2u : 0u) | (jar[2] < (T)0 ? 4u : 0u) | (jar[3] < (T)0 ? 8u : 0u)) << (4 * i);
     const T f0 = jar[0] < (T)0 ? -c.D * jar[0] : (T)0, f1 = jar[1] < (T)0 ? -c.D * jar[1] : (T)0;
     const T f2 = jar[2] < (T)0 ? -c.D * jar[2] : (T)0, f3 = jar[3] < (T)0 ? -c.D * jar[3] : (T)0;
     const T fw0 = mu * (f3 - f2), fw1 = mu * (f0 - f1), fw2 = f0 + f1 + f2 + f3;
+    fsum[0] += fw0; fsum[1] += fw1; fsum[2] += fw2;
 #pragma unroll
-    for (int p = 0; p < 6; p++) out7[p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
-    const T gA = c.Jx[6] * fw0 + c.Jy[6] * fw1 + c.Jz[6] * fw2, gB = c.Jx[7] * fw0 + c.Jy[7] * fw1 + c.Jz[7] * fw2;
+    for (int p = 0; p < 3; p++) out7[3 + p] += c.Jx[p] * fw0 + c.Jy[p] * fw1 + c.Jz[p] * fw2;
+    const T gA = c.Jx[3] * fw0 + c.Jy[3] * fw1 + c.Jz[3] * fw2, gB = c.Jx[4] * fw0 + c.Jy[4] * fw1 + c.Jz[4] * fw2;
     if (c.kind == QK_ROTOR) out7[6] += gA;
     else if ((JBQ_SPREAD && c.kind == QK_LEG_F)) { *ffa += gA; *ffb += gB; }
     else { *fla += gA; *flb += gB; }
   }
+  mulMTV(out7, fr.Rw, fsum);
   return mask;
 }
 
@@ -467,7 +473,7 @@ JB_HD uint32_t jbq_forces(const QConSet<T>& cs, T mu, T* out7, T* fla, T* flb, T
 // H: the leg block, and this lane's SHARE of the replicated block (see qarrow_factor).  W = sum over active rows of
 // D e e' has 5 distinct entries for the pyramid {z +- mu y, z -+ mu x}.
 template <typename T>
-JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H, T* F15) {
+JB_HD void jbq_hessian(const QConSet<T>& cs, const QFrame<T>& fr, T mu, jbq_mask_t mask, QArrow<T>& H, T* F15) {
   // F15: leg-block terms of this lane's FOREIGN contacts (ca[6], aa, cb[6], ab, bb of the owning lane)
   if (JBQ_SPREAD) {
 #pragma unroll
@@ -475,28 +481,34 @@ JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H, 
   }
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
-    const uint32_t m4 = mask >> (4 * i);
+    const uint32_t m4 = (uint32_t)(mask >> (4 * i));
     const T a0 = (m4 & 1u) ? (T)1 : (T)0, a1 = (m4 & 2u) ? (T)1 : (T)0;
     const T a2 = (m4 & 4u) ? (T)1 : (T)0, a3 = (m4 & 8u) ? (T)1 : (T)0;
     const T dm = c.D * mu;
     const T Wzz = c.D * (a0 + a1 + a2 + a3), Wyz = dm * (a0 - a1), Wxz = dm * (a3 - a2);
     const T Wyy = dm * mu * (a0 + a1), Wxx = dm * mu * (a2 + a3);
+    // full rows: the three linear entries are the shared Rw rows, the other five come from the slot
+    T jx[8], jy[8], jz[8];
+#pragma unroll
+    for (int q = 0; q < 3; q++) { jx[q] = fr.Rw[q]; jy[q] = fr.Rw[3 + q]; jz[q] = fr.Rw[6 + q]; }
+#pragma unroll
+    for (int q = 0; q < 5; q++) { jx[3 + q] = c.Jx[q]; jy[3 + q] = c.Jy[q]; jz[3 + q] = c.Jz[q]; }
     T Gx[8], Gy[8], Gz[8];
 #pragma unroll
     for (int q = 0; q < 8; q++) {
-      Gx[q] = Wxx * c.Jx[q] + Wxz * c.Jz[q];
-      Gy[q] = Wyy * c.Jy[q] + Wyz * c.Jz[q];
-      Gz[q] = Wxz * c.Jx[q] + Wyz * c.Jy[q] + Wzz * c.Jz[q];
+      Gx[q] = Wxx * jx[q] + Wxz * jz[q];
+      Gy[q] = Wyy * jy[q] + Wyz * jz[q];
+      Gz[q] = Wxz * jx[q] + Wyz * jy[q] + Wzz * jz[q];
     }
 #pragma unroll
     for (int p = 0; p < 6; p++)
 #pragma unroll
-      for (int q = 0; q <= p; q++) H.R[JBQ_TRI(p, q)] += c.Jx[p] * Gx[q] + c.Jy[p] * Gy[q] + c.Jz[p] * Gz[q];
+      for (int q = 0; q <= p; q++) H.R[JBQ_TRI(p, q)] += jx[p] * Gx[q] + jy[p] * Gy[q] + jz[p] * Gz[q];
     T hA[7], hB[8];      // H[A][0..5], H[A][A]; H[B][0..5], H[B][A], H[B][B]
 #pragma unroll
-    for (int q = 0; q < 7; q++) hA[q] = c.Jx[6] * Gx[q] + c.Jy[6] * Gy[q] + c.Jz[6] * Gz[q];
+    for (int q = 0; q < 7; q++) hA[q] = jx[6] * Gx[q] + jy[6] * Gy[q] + jz[6] * Gz[q];
 #pragma unroll
-    for (int q = 0; q < 8; q++) hB[q] = c.Jx[7] * Gx[q] + c.Jy[7] * Gy[q] + c.Jz[7] * Gz[q];
+    for (int q = 0; q < 8; q++) hB[q] = jx[7] * Gx[q] + jy[7] * Gy[q] + jz[7] * Gz[q];
     if (c.kind == QK_ROTOR) {
 #pragma unroll
       for (int q = 0; q < 6; q++) H.cm[q] += hA[q];
@@ -515,9 +527,9 @@ JB_HD void jbq_hessian(const QConSet<T>& cs, T mu, uint32_t mask, QArrow<T>& H, 
 }
 
 // this lane's part of phi'(alpha) - (g1 + alpha g2) and of phi''(alpha) - g2; returns the active mask at alpha
-template <typename T> JB_HD uint32_t jbq_ls_local(const QConSet<T>& cs, T mu, T alpha, T* d_out, T* h_out) {
+template <typename T> JB_HD jbq_mask_t jbq_ls_local(const QConSet<T>& cs, T mu, T alpha, T* d_out, T* h_out) {
   T d = 0, h = 0;
-  uint32_t mask = 0;
+  jbq_mask_t mask = 0;
   for (int i = 0; i < cs.n; i++) {
     const QCon<T>& c = cs.c[i];
     T jar[4], jv[4];
@@ -526,7 +538,7 @@ template <typename T> JB_HD uint32_t jbq_ls_local(const QConSet<T>& cs, T mu, T 
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       T x = jar[r] + alpha * jv[r];
-      if (x < (T)0) { d += c.D * x * jv[r]; h += c.D * jv[r] * jv[r]; mask |= 1u << (4 * i + r); }
+      if (x < (T)0) { d += c.D * x * jv[r]; h += c.D * jv[r] * jv[r]; mask |= (jbq_mask_t)1 << (4 * i + r); }
     }
   }
   *d_out = d; *h_out = h;
@@ -936,11 +948,11 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     qarrow_mul(cm, Ma, Mx, a);
     T laf = 0, lbf = 0;                       // leg entries of the lane that owns this lane's foreign contacts
     if (JBQ_SPREAD && wf) { laf = cm.get(a.la, hv); lbf = cm.get(a.lb, hv); }
-    jbq_apply_all(cs, a, 0, laf, lbf);
+    jbq_apply_all(cs, fr, a, 0, laf, lbf);
     const T scale = (T)1 / (g[G_MEANINERTIA] * (T)JB_NV);
     const int maxit = JbEps<T>::newton_iters();
     bool done = !has_con, full_prev = false, exact = false;
-    uint32_t mask_prev = 0xffffffffu;
+    jbq_mask_t mask_prev = ~(jbq_mask_t)0;
     // Each trip: (1) forces at the current point, gradient, convergence test; (2) Hessian, Newton direction;
     // (3) exact line search; (4) move.  The final pass through (1) leaves the constraint force of the solution --
     // unless the step just taken was a full Newton step inside one active set (the usual case from a good warm start):
@@ -949,7 +961,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     for (int trip = 0;; trip++) {
       if (trip > 0 && !cm.loop_any(!done)) break;
       T f8[8], fla, flb, ffa, ffb;
-      const uint32_t mask = jbq_forces(cs, mu, f8, &fla, &flb, &ffa, &ffb);
+      const jbq_mask_t mask = jbq_forces(cs, fr, mu, f8, &fla, &flb, &ffa, &ffb);
       if (JBQ_SPREAD && wf) {                 // leg-dof forces of foreign contacts go home to lane hv
         cm.sum2(ffa, ffb);
         if (lane == hv) { fla += ffa; flb += ffb; }
@@ -984,7 +996,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       }
       {
         T F15[15];
-        jbq_hessian(cs, mu, mask, H, F15);
+        jbq_hessian(cs, fr, mu, mask, H, F15);
         if (JBQ_SPREAD && wf) {               // and so do their leg-block Hessian terms
           cm.sumN(F15, 15);
           if (lane == hv) {
@@ -1005,13 +1017,13 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       QVec<T> Mv;
       qarrow_mul(cm, Mv, Mx, search);
       if (JBQ_SPREAD && wf) { laf = cm.get(search.la, hv); lbf = cm.get(search.lb, hv); }
-      jbq_apply_all(cs, search, 1, laf, lbf);
+      jbq_apply_all(cs, fr, search, 1, laf, lbf);
       cm.phase_sync(10);
       QVec<T> res = Ma; qv_axpy(res, (T)-1, fs);
       // g1 = s.(Ma - fs), g2 = s.Mv, d0 = s.grad (= phi'(0)); at alpha = 1: contact part of phi' and phi''
       T red[6];
       red[0] = qv_dot_leg(search, res); red[1] = qv_dot_leg(search, Mv); red[2] = qv_dot_leg(search, grad);
-      uint32_t m1 = jbq_ls_local(cs, mu, (T)1, &red[3], &red[4]);
+      jbq_mask_t m1 = jbq_ls_local(cs, mu, (T)1, &red[3], &red[4]);
       red[5] = m1 == mask ? (T)0 : (T)1;
       cm.sumN(red, 6);
       const T g1 = red[0] + qv_dot_rep(search, res), g2 = red[1] + qv_dot_rep(search, Mv);

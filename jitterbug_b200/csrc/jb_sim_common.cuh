@@ -27,7 +27,7 @@ struct JbDev {
   float *qpos, *qvel, *warm, *target;
   int *rev, *task, *step_count, *episode;
   unsigned char* reset_next;        // 0: stepping, 1: the next STEP resets the env, 2: reset earlier in the running control step
-  unsigned long long* counters;     // 5
+  unsigned long long* counters;     // 16: [0-4] see jb_sim_get_counters, [5-7] self-clearance monitor, [8-15] phase timers
   const int* perm;                  // slot -> env: quad `slot` of the grid simulates env perm[slot] (NULL = identity)
   int4* load;                       // per env, written by every STEP launch: how heavy the env's control step was
   const float* packed;              // [JBP_SIZE] (shared model) or [N][JBP_SIZE] (per-env models)
@@ -56,6 +56,9 @@ cudaError_t jb_launch_sim(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st
 cudaError_t jb_configure_kernels(void);
 cudaError_t jb_launch_sim_perenv(const JbDev& d, const JbLaunchArgs& a, cudaStream_t st);
 cudaError_t jb_configure_kernels_perenv(void);   // per device: opt in to the dynamic shared memory the per-env mode needs
+// jb_monitor.cu: conservative self-clearance of every env at its current state (counters 5-7; optional per-env output)
+#define JB_MONITOR_PERIOD 8          /* jb_sim_step runs the monitor every this many control steps */
+cudaError_t jb_launch_self_clearance(const JbDev& d, float* out_dev, cudaStream_t st);
 // jb_sort.cu: stable counting sort of the env ids by a small key of their last load record (the step kernel's slot order)
 #define JB_SORT_BUCKETS 16
 #define JB_SORT_MIN_ENVS (4 * 148 * JB_ENVS_PER_BLOCK)   /* four waves of full CTAs on a 148-SM part */

@@ -3,6 +3,10 @@
 // xor-butterfly summation order ((x_l + x_{l^1}) + (x_{l^2} + x_{l^3})), so the host result is what the kernel computes
 // (in fp64 for algorithmic parity, in fp32 for rounding behaviour).  Never loaded by the product package.
 #define JBQ_DEBUG_COUNT 1
+#ifndef JBQ_HOST_PHASE_HOOK
+#define JBQ_HOST_PHASE_HOOK(lane, p) ((void)0)      /* quadflops.cpp: attribute counted flops to (lane, phase) */
+#define JBQ_HOST_LANE_HOOK(lane) ((void)0)
+#endif
 #include "../../jitterbug_b200/csrc/jb_quad.cuh"
 #include "../../jitterbug_b200/csrc/jb_task.cuh"
 #include <string.h>
@@ -53,7 +57,7 @@ template <typename T> struct FiberComm {
   int isum(int v) { T x = (T)v; exchange(&x, 1); return (int)(x + (T)0.5); }
   bool warp_any(bool p) { return isum(p ? 1 : 0) > 0; }   // the emulated "warp" is one quad
   bool loop_any(bool p) { return warp_any(p); }
-  void phase_sync(int) {}
+  void phase_sync(int p) { JBQ_HOST_PHASE_HOOK(lane, p); }
 };
 
 template <typename T> struct Job {
@@ -75,8 +79,7 @@ template <typename T> void fiber_main(int lane) {
   g_s->done[lane] = true;
   swapcontext(&g_s->fib[lane], &g_s->main_ctx);
 }
-void fiber_entry_d(int lane) { fiber_main<double>(lane); }
-void fiber_entry_f(int lane) { fiber_main<float>(lane); }
+template <typename T> void fiber_entry(int lane) { fiber_main<T>(lane); }
 
 template <typename T> void run_quad(Job<T>& J) {
   Sched S;
@@ -89,14 +92,14 @@ template <typename T> void run_quad(Job<T>& J) {
     S.fib[l].uc_stack.ss_sp = S.stacks[l].data();
     S.fib[l].uc_stack.ss_size = S.stacks[l].size();
     S.fib[l].uc_link = &S.main_ctx;
-    if (sizeof(T) == 8) makecontext(&S.fib[l], (void (*)())fiber_entry_d, 1, l);
-    else makecontext(&S.fib[l], (void (*)())fiber_entry_f, 1, l);
+    makecontext(&S.fib[l], (void (*)())fiber_entry<T>, 1, l);
   }
   for (;;) {
     bool all = true;
     for (int l = 0; l < 4; l++) {
       if (S.done[l]) continue;
       all = false;
+      JBQ_HOST_LANE_HOOK(l);
       swapcontext(&S.main_ctx, &S.fib[l]);
     }
     if (all) break;

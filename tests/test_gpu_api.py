@@ -332,3 +332,58 @@ def test_step_host_equals_device_step_with_pageable_and_pinned_buffers():
         for o, r, s in ((oh, rh, sh), (op, rp, sp)):
             assert np.array_equal(o, od.cpu().numpy()) and np.array_equal(r, rd.cpu().numpy())
             assert np.array_equal(s, sd.cpu().numpy())
+
+
+def test_self_clearance_monitor_matches_numpy_and_stays_positive(compiled_model):
+    """The on-device self-clearance monitor (csrc/jb_monitor.cu) against a numpy evaluation of the same conservative
+    covers on the oracle's forward kinematics; and over a contact-rich batch no non-floor pair ever comes close."""
+    _need_gpu()
+    import itertools
+    from jitterbug_b200 import BatchedJitterbugEnv, mjcf
+    from oracle import oracle as O
+    import test_self_collision_clearance as T
+    cm = compiled_model
+    N = 4096
+    env = BatchedJitterbugEnv("move_from_origin", num_envs=N, seed=12)
+    env.reset()
+    g = torch.Generator(device=env.device).manual_seed(5)
+    for _ in range(120):
+        env.step(torch.rand(N, device=env.device, generator=g) * 2 - 1)
+    res = env.self_clearance(per_env=True)
+    clr = res["clearance"].cpu().numpy()
+    assert res["checked"] >= N * (120 // 8) and res["below_zero"] == 0
+    assert res["min_clearance_m"] > 1e-4 and clr.min() > 1e-4
+    qpos = env.get_state()[0].cpu().numpy().astype(np.float64)
+    moving = [gg for gg in range(cm.ngeom) if 0 < cm.geom_bodyid[gg] < cm.nbody - 1]
+    pairs = [(a, b) for a, b in itertools.combinations(moving, 2)
+             if cm.geom_bodyid[a] != cm.geom_bodyid[b] and cm.body_parentid[cm.geom_bodyid[a]] != cm.geom_bodyid[b]
+             and cm.body_parentid[cm.geom_bodyid[b]] != cm.geom_bodyid[a]]
+    sim = O.OracleSim(cm)
+
+    def cover(gg):
+        pos = sim.view("geom_xpos")[gg].copy()
+        mat = sim.view("geom_xmat")[gg].reshape(3, 3)
+        t, size = cm.geom_type[gg], cm.geom_size[gg]
+        if t == mjcf.GEOM_CYLINDER:
+            return pos - mat[:, 2] * size[1], pos + mat[:, 2] * size[1], size[0]
+        if t == mjcf.GEOM_SPHERE:
+            return pos, pos, size[0]
+        if t == mjcf.GEOM_BOX:
+            return pos, pos, float(np.linalg.norm(size))
+        return ("ellipsoid", pos, mat, size.copy())
+
+    def pair_clearance(A, B):
+        if isinstance(A[0], str) or isinstance(B[0], str):
+            (_, c, R, sz), (p, q, r) = (A, B) if isinstance(A[0], str) else (B, A)
+            a, b = R.T @ (p - c) / sz, R.T @ (q - c) / sz        # the capsule's axis in unit-sphere coordinates
+            u = b - a
+            tt = np.clip(-(a @ u) / (u @ u), 0, 1) if u @ u > 1e-20 else 0.0
+            far = T._seg_seg(p - c, q - c, np.zeros(3), np.zeros(3)) - sz.max()
+            return max(sz.min() * (np.linalg.norm(a + tt * u) - 1.0), far) - r
+        return T._seg_seg(A[0], A[1], B[0], B[1]) - A[2] - B[2]
+    for e in range(0, N, 128):
+        sim.set_state(qpos[e], np.zeros(15))
+        sim.step1()
+        prox = {gg: cover(gg) for gg in moving}
+        want = min(pair_clearance(prox[a], prox[b]) for a, b in pairs)
+        assert abs(clr[e] - want) < 2e-6, (e, clr[e], want)
