@@ -21,6 +21,7 @@
 namespace {
 struct Prim { float a[3], b[3], r; int body; };      // segment a-b swept by a sphere of radius r (a == b: a sphere)
 struct Ell { float c[3], R[9], s[3]; int body; };    // centre, rotation (local -> root frame), semi-axes
+__device__ float seg_seg_dist2(const float* p1, const float* q1, const float* p2, const float* q2);
 
 // lower bound of the distance between the capsule p and the ellipsoid e (see the head of this file)
 __device__ float ell_clearance(const Ell& e, const Prim& p) {

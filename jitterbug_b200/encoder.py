@@ -111,6 +111,8 @@ class ObservationEncoder:
         """obs ``[N, >= obs_dim]`` float32 CUDA -> ``[N, out_dim]`` (latent, then the passed-through features)."""
         if obs.device != self.device or obs.dtype != torch.float32 or obs.dim() != 2 or obs.stride(1) != 1:
             raise ValueError("obs must be a float32 [N, D] tensor with unit inner stride on the encoder's device")
+        if obs.shape[1] < self.desc.obs_dim:
+            raise ValueError(f"obs has {obs.shape[1]} features per env, the encoder reads {self.desc.obs_dim}")
         n = obs.shape[0]
         if out is None:
             out = torch.empty((n, self.out_dim), dtype=torch.float32, device=self.device)

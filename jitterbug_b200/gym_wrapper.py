@@ -2,7 +2,9 @@
 
 The reference subclasses ``dm2gym.DMControlEnv``: ``step(a) -> (observation, reward, done, {})`` with
 ``done = timestep.last()``, ``reset() -> observation`` (SURVEY.md section 3.4).  ``gym`` / ``dm2gym`` are not needed;
-spaces are provided through ``gym.spaces`` when it is importable and through a tiny ``Box`` otherwise.  There is no
+spaces are provided through ``gym.spaces`` when it is importable and through tiny ``Box`` / ``Dict`` look-alikes
+otherwise.  Like ``dm2gym``, ``observation_space`` describes exactly what ``reset`` / ``step`` return: a ``Dict`` space
+keyed like the observation dict (one ``"observations"`` entry for ``flat_observation=True`` environments).  There is no
 renderer in the batched simulator: ``render`` keeps the reference's frame counting and is otherwise a no-op.
 """
 
@@ -26,6 +28,23 @@ except Exception:  # noqa: BLE001
             return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
 
 
+try:  # pragma: no cover
+    _Dict = _spaces.Dict
+except Exception:  # noqa: BLE001
+    class _Dict(dict):
+        """Minimal ``gym.spaces.Dict``: an ordered mapping of sub-spaces."""
+
+        @property
+        def spaces(self):
+            return self
+
+        def sample(self):
+            return type(self)((k, v.sample()) for k, v in self.items())
+
+        def contains(self, x):
+            return set(x) == set(self) and all(self[k].contains(np.asarray(x[k], dtype=self[k].dtype)) for k in self)
+
+
 class JitterbugGymEnv:
     """A Gym-style env around a Jitterbug ``Environment``.
 
@@ -44,10 +63,9 @@ class JitterbugGymEnv:
         spec = env.action_spec()
         self.action_space = _Box(spec.minimum.astype(np.float32), spec.maximum.astype(np.float32), shape=spec.shape,
                                  dtype=np.float32)
-        ospec = env.observation_spec()
-        self._flat = "observations" in ospec and len(ospec) == 1
-        dim = sum(int(np.prod(v.shape)) for v in ospec.values())
-        self.observation_space = _Box(-np.inf, np.inf, shape=(dim,), dtype=np.float32)
+        import collections
+        self.observation_space = _Dict(collections.OrderedDict(
+            (k, _Box(-np.inf, np.inf, shape=tuple(v.shape), dtype=np.float64)) for k, v in env.observation_spec().items()))
         self.reward_range = (0.0, 1.0)
 
     def _obs(self, ts):

@@ -49,9 +49,18 @@ def test_flat_observation_and_gym_wrapper():
     assert env.num_envs == 1
     obs = env.reset()
     assert list(obs) == ["observations"] and obs["observations"].shape == (19,)
+    # the declared space is the space of what reset / step return (dm2gym exposes a matching Dict space)
+    assert list(env.observation_space.spaces) == ["observations"] and env.observation_space.contains(obs)
+    assert env.observation_space.spaces["observations"].shape == (19,)
     for t in range(5):
         obs, reward, done, info = env.step(0.8)
-        assert not done and info == {} and 0 <= reward <= 1
+        assert not done and info == {} and 0 <= reward <= 1 and env.observation_space.contains(obs)
+    env.close()
+    env = JitterbugGymEnv(suite.load("jitterbug", "face_direction", task_kwargs=dict(random=0)))
+    obs = env.reset()
+    assert list(env.observation_space.spaces) == list(obs) == ["position", "velocity", "motor_position", "motor_velocity",
+                                                                "angle_to_target"]
+    assert env.observation_space.contains(obs) and env.action_space.shape == (1,)
     env.close()
 
 
