@@ -133,5 +133,5 @@ def test_encoder_rejects_bad_arguments():
     enc = ObservationEncoder(16, [(w, b)], ["tanh"])
     with pytest.raises(ValueError):
         enc(torch.zeros(4, 16))                                             # host tensor
-    with pytest.raises(RuntimeError):
+    with pytest.raises(ValueError):
         enc(torch.zeros(4, 8, device="cuda"))                               # obs narrower than obs_dim
