@@ -359,5 +359,8 @@ cudaError_t JB_CONFIGURE(void) {
   // (CTAs larger than 496 threads exceed the 227 KB limit in per-env mode and are rejected at launch)
   size_t need = (size_t)JB_ENVS_PER_BLOCK * JBP_ENV_STRIDE * sizeof(float);
   if (need > 227 * 1024) need = 227 * 1024;
+#ifdef JB_CARVEOUT_L1
+  cudaFuncSetAttribute(JB_SIM_KERNEL, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+#endif
   return cudaFuncSetAttribute(JB_SIM_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
 }

@@ -3,12 +3,17 @@
  * control.Environment(physics, task, control_timestep=0.01); each env.step() runs
  * 50 x physics.step() == mj_step2; mj_step1 of MuJoCo 2.0 on jitterbug_dmc/jitterbug.xml).
  *
- * PARITY UNPINNED: MuJoCo / dm_control are third-party, un-vendored dependencies of the reference
- * (setup.py:10-14 pins dm_control @ 09b27a0 => MuJoCo 2.0) and are not installed here; the reference
- * holds no tests or golden vectors.  This file restates MuJoCo's published
- * algorithm (Computation chapter + the open-sourced engine_*.c structure) from memory and is anchored
- * by analytic known-answer tests and an independent numpy finite-difference dynamics check
- * (tests/test_oracle_*.py), not by MuJoCo itself.
+ * PINNING STATUS.  Pinned to outputs of the reference's OWN code (tests/golden/reference_*.npz, produced by
+ * tests/golden/make_reference_golden.py executing /root/reference's jitterbug.py / heuristic_policies.py /
+ * augmented_jitterbug.py; checked by tests/test_reference_golden.py): the task layer of this file
+ * (jbo_task_obs_reward: Physics helpers, observation, rewards) and the heuristic policies (jbo_heuristic).
+ * PARITY UNPINNED for the step pipeline itself (mj_step2; mj_step1): MuJoCo / dm_control are third-party,
+ * un-vendored dependencies of the reference (setup.py:10-14 pins dm_control @ 09b27a0 => MuJoCo 2.0) and are
+ * not installed here, and the reference holds no tests or golden vectors for it.  That
+ * part restates MuJoCo's published algorithm (Computation chapter + the open-sourced engine_*.c structure)
+ * from memory and is anchored by analytic known-answer tests and an independent numpy finite-difference
+ * dynamics check (tests/test_oracle_*.py); tests/test_mujoco_parity.py diffs it against a real MuJoCo
+ * wherever one is importable (it skips in this project's containers).
  *
  * Nothing in the product path (jitterbug_b200/) links or calls this file.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.
