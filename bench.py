@@ -326,6 +326,7 @@ def run_cuda(args):
         vec = VecJitterbugEnv(BatchedJitterbugEnv("move_to_pose", num_envs=E_r, device=dev, seed=args.seed,
                                                   env_id_offset=rank * E_r))
         torch.manual_seed(rank)
+        torch.backends.cuda.matmul.allow_tf32 = True      # the policy's three small GEMMs on the tensor cores (TF32)
         policy = ActorCritic(vec.obs_dim).to(dev)
         buf = RolloutBuffer(horizon, E_r, vec.obs_dim, dev)
         o = vec.reset()
@@ -342,7 +343,7 @@ def run_cuda(args):
         ms = allmax(e0.elapsed_time(e1))
         other["config5_ppo_collection_move_to_pose"] = {
             "value": world * E_r * horizon / (ms * 1e-3), "unit": "env+policy control_steps/s", "envs_per_gpu": E_r,
-            "workload": "move_to_pose, ActorCritic 350-250 on device, action + log-prob + value per step into the on-device "
+            "workload": "move_to_pose, ActorCritic 350-250 on device (TF32 matmuls), action + log-prob + value per step into the on-device "
                         "buffer, GAE at the end of the horizon, CUDA-graph replay of policy + env step",
             "horizon": horizon, "burn_in_steps": b_o}
         vec.close()

@@ -35,6 +35,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     env = make_sharded_env(args.task, args.envs, seed=0, time_limit=args.time_limit)
     vec = VecJitterbugEnv(env)
+    torch.backends.cuda.matmul.allow_tf32 = True          # the policy's small GEMMs on the tensor cores (TF32)
     policy = ActorCritic(env.obs_dim).to(env.device)
     # burn-in: from reset the Jitterbugs are airborne / spinning up, which is cheaper than the steady state
     obs = vec.reset()
