@@ -74,17 +74,18 @@ def _measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons.  The sampler is started early (nvidia-smi needs a moment to come up) and
+    every sample carries nvidia-smi's own timestamp; ``stop(t0, t1)`` keeps the samples taken inside the timed region."""
 
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.proc = None
         self.lines = []
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(index), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(index), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -95,9 +96,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)                                  # let the last samples of the region arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -107,13 +110,16 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); smax.append(float(parts[1])); power.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t0 is not None and not (t0 <= ts <= t1):
+                    continue
+                sm.append(float(parts[1])); smax.append(float(parts[2])); power.append(float(parts[3]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
+            for n, v in zip(names, parts[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
@@ -249,21 +255,23 @@ def run_cuda(args):
     def measure(env, action, burn_in, warmup, steps, sample_clocks=False):
         """Device-timed steady-state throughput of `steps` control steps (max over ranks) + per-step kernel times."""
         stream = torch.cuda.current_stream(dev)
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         for i in range(burn_in):
             env.step(action(i))
         for i in range(warmup):
             env.step(action(i))
         barrier()
         c0, l0 = env.counters(), env.launch_count()
-        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         barrier()
+        t_wall0 = time.time()
         ev[0].record(stream)
         for i in range(steps):
             env.step(action(i))
             ev[i + 1].record(stream)
         barrier()
-        clocks = sampler.stop() if sampler else None
+        t_wall1 = time.time()
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
         total_ms = allmax(ev[0].elapsed_time(ev[-1]))
         c1, l1 = env.counters(), env.launch_count()
         sub = max(c1["substeps"] - c0["substeps"], 1)
