@@ -44,9 +44,10 @@ typedef uint64_t jbq_mask_t;
 typedef uint32_t jbq_mask_t;
 #endif
 // JBQ_SPREAD: balance a heavy lane's leg contacts over its quad (see the leg phase of jbq_substep).  It shortens the
-// contact loops of the fullest lane from 4 to 2 trips, but costs ~800 instructions and 15 live accumulators: a gain where
-// registers are plentiful (per-env-model kernel, +10 %), a loss in the 168-register shared-model kernel (-7 %), so the
-// builds choose.  The host emulation keeps it on.
+// contact loops of the fullest lane from 4 to 2 trips, but costs ~800 instructions and 15 live accumulators.  It paid in
+// round 1's per-env-model kernel (+10 %); since the load sort packs heavy envs into CTAs of their own (jb_sort.cu) both
+// product builds compile it out (-16 % in the shared-model kernel, -9 % in the per-env one).  The host emulation keeps
+// it on, so the path stays tested.
 #ifndef JBQ_SPREAD
 #define JBQ_SPREAD 1
 #endif

@@ -8,13 +8,13 @@
 // This file is compiled twice (jitterbug_b200/build.py): as is for the shared-model kernel (384-thread CTAs, 168
 // registers), and with -DJB_PER_ENV_BUILD for the per-env-model kernel: there every env's 1.8 KB model is staged in shared
 // memory, which comes out of the L1 that caches the local-memory contact slots and spills, so that build trades CTA
-// size for registers (256-thread bound: ~229 registers, no spills), runs 256-thread CTAs and spreads a heavy lane's
-// contacts over its quad (JBQ_SPREAD, see jb_quad.cuh).
+// size for registers (256-thread bound: ~222 registers, no spills) and runs 256-thread CTAs.
 #ifdef JB_PER_ENV_BUILD
 #undef JB_BLOCK
 #define JB_BLOCK 256
 #ifndef JBQ_SPREAD
-#define JBQ_SPREAD 1          /* registers to spare here: see jb_quad.cuh */
+#define JBQ_SPREAD 0          /* spreading a heavy lane's contacts over its quad paid before the load sort (+3 %); with heavy
+                                 envs packed into their own CTAs it costs every other CTA: 9.3 -> 10.2 M steps/s without it */
 #endif
 #define JB_SIM_KERNEL jb_sim_kernel_perenv
 #define JB_LAUNCH_SIM jb_launch_sim_perenv

@@ -70,3 +70,8 @@ extern "C" void hq_count_flops(const double* P, double* qpos, double* qvel, doub
   for (int i = 0; i < 15; i++) { qvel[i] = v[i].v; warm[i] = w[i].v; }
   *algorithmic = alg; *executed = exe; *iters_out = it; *ncon_out = ncon;
 }
+
+// per-(lane, phase) counts of the last hq_count_flops call (diagnostics: which phases replicate how much)
+extern "C" void hq_flops_lane_phase(long long* out64) {
+  for (int l = 0; l < 4; l++) for (int p = 0; p < 16; p++) out64[16 * l + p] = g_flops_lane_phase[l][p];
+}

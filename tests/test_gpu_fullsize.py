@@ -64,3 +64,38 @@ def test_augmented_full_size_equals_small_batch_bit_for_bit():
         assert torch.isfinite(ob).all()
     # models differ from env to env: so do the trajectories of envs that start from the same pose statistics
     assert float((a[-1][0][:1024, 2] - a[-1][0][1024:2048, 2]).abs().max()) > 0
+
+
+def test_results_do_not_depend_on_slot_order_or_segmentation():
+    """The load-sorted slot order and the 10-sub-step segmentation of a control step are scheduling only: identity order
+    with one launch per step, the automatic sort (five segments, re-sorted after each) and random explicit permutations
+    give bit-identical observations, rewards, step types, states and device counters.  (The 1 Mi-env tests above compare
+    the default sorted path with small identity-ordered batches as well.)"""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    n = 16384
+    envs = [BatchedJitterbugEnv("move_to_pose", num_envs=n, seed=9, time_limit=0.3) for _ in range(3)]   # 30-step episodes
+    envs[0].set_slot_order("identity")
+    envs[1].set_slot_order("auto")
+    g = torch.Generator(device=envs[0].device).manual_seed(2)
+    envs[2].set_slot_order(torch.randperm(n, device=envs[0].device, generator=g).int())
+    for e in envs:
+        e.reset()
+    for k in range(70):                          # crosses two episode boundaries (LAST, then the reset step)
+        a = _actions(n, k, envs[0].device)
+        outs = [e.step(a) for e in envs]
+        for o in outs[1:]:
+            for x, y in zip(outs[0], o):
+                assert torch.equal(x, y), k
+        if k % 9 == 0:
+            envs[2].set_slot_order(torch.randperm(n, device=envs[0].device, generator=g).int())
+    for s0, s1, s2 in zip(*[e.get_state() for e in envs]):
+        assert torch.equal(s0, s1) and torch.equal(s0, s2)
+    assert envs[0].counters() == envs[1].counters() == envs[2].counters()
+    perm = envs[1].get_slot_order().long()
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, device=perm.device))
+    # the sort really orders by load: the load key of the envs is non-increasing along the slots (heaviest first)
+    ld = envs[1].load().long()
+    last = (ld[:, 3] >> 16)[perm]
+    assert int(last[: n // 20].float().mean() * 100) >= int(last[-n // 20:].float().mean() * 100)
+    assert envs[0].launch_count() < envs[1].launch_count()
