@@ -32,7 +32,12 @@ def _worker(rank, world, port, total, out):
         rng = np.random.default_rng(0)
         all_returns = rng.uniform(0, 1000, size=total)
         off, cnt = shard_envs(total, rank, world)
-        stats = gather_episode_stats(torch.from_numpy(all_returns[off:off + cnt]))
+        mine = torch.from_numpy(all_returns[off:off + cnt])
+        stats = gather_episode_stats(mine)
+        # the running-monitor form (rollout.VecJitterbugEnv accumulates these moments on the device)
+        moments = (torch.tensor(float(cnt), dtype=torch.float64), mine.sum(), (mine * mine).sum(), mine.min(), mine.max())
+        stats_m = gather_episode_stats(None, moments=moments)
+        assert stats_m == stats and float(moments[3]) == float(mine.min())      # inputs are not modified
         if rank == 0:
             out.put((stats, float(all_returns.mean()), float(all_returns.std()), float(all_returns.min()),
                      float(all_returns.max())))
