@@ -31,14 +31,17 @@
 #include "jb_task.cuh"
 
 #ifndef JB_SYNC_SUBSTEP
-#define JB_SYNC_SUBSTEP 1
+#define JB_SYNC_SUBSTEP 0       /* extra CTA barrier at the top of every sub-step: redundant next to the post-solver one (+2 %
+                                   without it since the load sort) */
 #endif
 #ifndef JB_BLOCK_NEWTON
 #define JB_BLOCK_NEWTON 0
 #endif
 #ifndef JB_PHASE_SYNC
-#define JB_PHASE_SYNC 0x52      /* bit p: barrier at phase boundary p (1..6; 8..11 inside the Newton loop need JB_BLOCK_NEWTON).
-                                   0x52 = after the leg phase, before the solver, after the solver: measured 1 % ahead of all six (0x7e) */
+#define JB_PHASE_SYNC 0x42      /* bit p: barrier at phase boundary p (1..6; 8..11 inside the Newton loop need JB_BLOCK_NEWTON).
+                                   0x42 = after the leg phase and after the solver: two whole-CTA barriers per sub-step keep
+                                   the warps in the same code region; measured ahead of all six (0x7e, round 1's setting)
+                                   by 2 % once the load sort is on (profiles/README.md) */
 #endif
 #ifndef JB_MIN_BLOCKS
 #define JB_MIN_BLOCKS 1
