@@ -312,13 +312,54 @@ JBQ_EMIT_ATTR void jbq_emit(const T* g, QConSet<T>& cs, const QFrame<T>& fr, con
 
 #define JBQ_EMIT(geom, x, dist) jbq_emit<T>(g, cs, fr, b, (geom), (x), (dist), rep, lane)
 
+// the same, always inlined: for the one hot call site (a foot on the floor is THE common contact), see jbq_col_sphere
+template <typename T>
+JB_HD void jbq_emit_hot(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* x, T dist,
+                        const QReport<T>* rep, int lane) {
+  if (!(dist < (T)0)) return;
+  int i = cs.n;
+  if (i >= JBQ_CAP) { cs.overflow = 1; return; }
+  cs.n = i + 1;
+  QCon<T>& c = cs.c[i];
+  if (b.defer) {
+    c.ww[0] = x[0]; c.ww[1] = x[1]; c.ww[2] = x[2]; c.ar0 = dist; c.kind = geom | (b.lower ? JBQ_TAG_LOWER : 0);
+    return;
+  }
+  c.kind = b.kind;
+  T ja[3] = {0, 0, 0}, jb[3] = {0, 0, 0}, r[3];
+  if (b.kind != QK_ROOT) {
+    sub3(r, x, b.p1); cross3(ja, b.a1, r);
+    if (b.lower) { sub3(r, x, b.p2); cross3(jb, b.a2, r); }
+  }
+  T* const rows[3] = {c.Jx, c.Jy, c.Jz};
+  T vw[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    T* J = rows[k];
+    const T* rk = fr.Rw + 3 * k;
+    cross3(J, x, rk);
+    J[3] = dot3(rk, ja); J[4] = dot3(rk, jb);
+    vw[k] = dot3(rk, fr.vr) + dot3(J, fr.w) + J[3] * b.qd1 + J[4] * b.qd2;
+  }
+  T imp = jbq_impedance<T>(g + G_SOLIMP, dist);
+  T mu = g[G_FRIC];
+  T Rpy = (T)2 * mu * mu / g[G_IMPRATIO] * ((T)1 - imp) / imp * b.invw * ((T)1 + mu * mu);
+  c.D = (T)1 / jb_max(Rpy, (T)1e-15);
+  c.ar0 = -g[G_SOLK] * imp * dist;
+  c.uref[0] = -g[G_SOLB] * vw[0]; c.uref[1] = -g[G_SOLB] * vw[1]; c.uref[2] = -g[G_SOLB] * vw[2];
+  if (rep) { rep->geom[(lane * JBQ_CAP + i) * rep->stride] = geom; rep->dist[(lane * JBQ_CAP + i) * rep->stride] = dist; }
+}
+
 template <typename T>
 JB_HD void jbq_col_sphere(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c, T r,
-                          const QReport<T>* rep, int lane) {
+                          const QReport<T>* rep, int lane, bool hot = false) {
   T dist = fr.pz + dot3(fr.n, c) - r;
   if (dist > (T)0) return;
   T s = r + (T)0.5 * dist;
   T x[3] = {c[0] - fr.n[0] * s, c[1] - fr.n[1] * s, c[2] - fr.n[2] * s};
+  // a foot on the floor is THE common contact: building it in line instead of through the out-of-line jbq_emit saves the
+  // call and the round trip of its by-reference arguments through local memory (+6 % on the whole step)
+  if (hot) { jbq_emit_hot<T>(g, cs, fr, b, geom, x, dist, rep, lane); return; }
   JBQ_EMIT(geom, x, dist);
 }
 
@@ -690,7 +731,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       // foot sphere (lower body)
       gh[0] = LL(L_FT_C); gh[1] = LL(L_FT_C + 1); gh[2] = LL(L_FT_C + 2);
       sub3(r, gh, p2h); mulMV(t, R12, r); add3(c, p2, t);
-      jbq_col_sphere<T>(g, cs, fr, bl, (int)LL(L_FT_ID), c, LL(L_FT_R), rep, lane);
+      jbq_col_sphere<T>(g, cs, fr, bl, (int)LL(L_FT_ID), c, LL(L_FT_R), rep, lane, true);
       // lower cylinder
       gh[0] = LL(L_LC_C); gh[1] = LL(L_LC_C + 1); gh[2] = LL(L_LC_C + 2);
       sub3(r, gh, p2h); mulMV(t, R12, r); add3(c, p2, t);
