@@ -20,7 +20,9 @@
 
 // cold paths (contact creation, cylinder / box / ellipsoid narrow phase) are real function calls on the device: they
 // run rarely and inlining them at every call site made the kernel several times larger than the instruction cache
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && defined(JBQ_INLINE_ALL)      /* tuning: every narrow-phase routine in line */
+#define JB_COLD __host__ __device__ __forceinline__
+#elif defined(__CUDACC__)
 #define JB_COLD __host__ __device__ __noinline__
 #else
 #define JB_COLD inline
@@ -363,9 +365,11 @@ JB_HD void jbq_col_sphere(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const
   JBQ_EMIT(geom, x, dist);
 }
 
-// mjc_PlaneCylinder; xax is only needed when the axis is exactly parallel to the floor normal
-template <typename T>
-JB_COLD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+// mjc_PlaneCylinder; xax is only needed when the axis is exactly parallel to the floor normal.  HOT: everything in line
+// (the lower-leg cylinder of a leg lying on the floor, see the leg phase); otherwise the emits are calls
+#define JBQ_EMIT_SEL(geom, x, dist) do { if (HOT) jbq_emit_hot<T>(g, cs, fr, b, (geom), (x), (dist), rep, lane); else JBQ_EMIT(geom, x, dist); } while (0)
+template <typename T, bool HOT>
+JB_HD void jbq_col_cylinder_impl(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
                             const T* ax_in, const T* xax, T r, T hl, const QReport<T>* rep, int lane) {
   T dist0 = fr.pz + dot3(fr.n, c);
   T ax[3] = {ax_in[0], ax_in[1], ax_in[2]};
@@ -387,12 +391,12 @@ JB_COLD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, c
   T x[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] + ax[k] - fr.n[k] * d1 * (T)0.5;
-  JBQ_EMIT(geom, x, d1);
+  JBQ_EMIT_SEL(geom, x, d1);
   T d2 = dist0 - prjaxis + prjvec;
   if (d2 <= (T)0) {
 #pragma unroll
     for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] - ax[k] - fr.n[k] * d2 * (T)0.5;
-    JBQ_EMIT(geom, x, d2);
+    JBQ_EMIT_SEL(geom, x, d2);
   }
   T d3 = dist0 + prjaxis - prjvec * (T)0.5;
   if (d3 <= (T)0) {
@@ -404,11 +408,18 @@ JB_COLD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, c
     v1[0] *= s; v1[1] *= s; v1[2] *= s;
 #pragma unroll
     for (int k = 0; k < 3; k++) x[k] = c[k] + v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
-    JBQ_EMIT(geom, x, d3);
+    JBQ_EMIT_SEL(geom, x, d3);
 #pragma unroll
     for (int k = 0; k < 3; k++) x[k] = c[k] - v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
-    JBQ_EMIT(geom, x, d3);
+    JBQ_EMIT_SEL(geom, x, d3);
   }
+}
+
+#undef JBQ_EMIT_SEL
+template <typename T>
+JB_COLD void jbq_col_cylinder(const T* g, QConSet<T>& cs, const QFrame<T>& fr, const QBody<T>& b, int geom, const T* c,
+                            const T* ax_in, const T* xax, T r, T hl, const QReport<T>* rep, int lane) {
+  jbq_col_cylinder_impl<T, false>(g, cs, fr, b, geom, c, ax_in, xax, r, hl, rep, lane);
 }
 
 template <typename T>
@@ -725,8 +736,13 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     // collision: this leg's geoms.  Cheap height test on the sphere centres / cylinder bounding spheres first.
     {
       // the leg's contacts are parked raw (defer) and built after jbq_spread has balanced them over the quad
-      QBody<T> bu = {QK_LEG, a1, p1, s.va, a2, p2, (T)0, false, LL(L_INVWU), JBQ_SPREAD != 0};
-      QBody<T> bl = {QK_LEG, a1, p1, s.va, a2, p2, s.vb, true, LL(L_INVWL), JBQ_SPREAD != 0};
+      // The out-of-line collision routines take the frame and the body description by reference, i.e. through local
+      // memory.  They run rarely, so each call site makes its own copy (JBQ_COLD_ARGS) inside its branch: `fr` and the
+      // description used by the in-line foot path then never leave the registers on the common path.
+#define JBQ_COLD_ARGS(body) const QFrame<T> frc = fr; const QBody<T> bc = body
+#define JBQ_BODY_U {QK_LEG, a1, p1, s.va, a2, p2, (T)0, false, LL(L_INVWU), JBQ_SPREAD != 0}
+#define JBQ_BODY_L {QK_LEG, a1, p1, s.va, a2, p2, s.vb, true, LL(L_INVWL), JBQ_SPREAD != 0}
+      const QBody<T> bl = JBQ_BODY_L;
       T c[3], gh[3], gv[3], ax[3], xa[3];
       // foot sphere (lower body)
       gh[0] = LL(L_FT_C); gh[1] = LL(L_FT_C + 1); gh[2] = LL(L_FT_C + 2);
@@ -740,13 +756,29 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
           gv[0] = LL(L_LC_AX); gv[1] = LL(L_LC_AX + 1); gv[2] = LL(L_LC_AX + 2); mulMV(ax, R12, gv);
           gv[0] = LL(L_LC_XA); gv[1] = LL(L_LC_XA + 1); gv[2] = LL(L_LC_XA + 2); mulMV(xa, R12, gv);
-          jbq_col_cylinder<T>(g, cs, fr, bl, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
+          // in line as well: a leg lying on the floor (the heavy envs) comes through here every sub-step; measured
+          // +4 % on the whole step.  Knee / upper cylinder / extra geoms in line too: no further gain (JBQ_UPPER_INLINE,
+          // JBQ_INLINE_ALL), so those stay calls.
+#ifndef JBQ_LCYL_CALL
+          jbq_col_cylinder_impl<T, true>(g, cs, fr, bl, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
+#else
+          JBQ_COLD_ARGS(JBQ_BODY_L);
+          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
+#endif
         }
       }
         // knee sphere (upper body)
       gh[0] = LL(L_KN_C); gh[1] = LL(L_KN_C + 1); gh[2] = LL(L_KN_C + 2);
       sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
-      jbq_col_sphere<T>(g, cs, fr, bu, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane);
+#ifdef JBQ_UPPER_INLINE
+      const QBody<T> bu = JBQ_BODY_U;
+      jbq_col_sphere<T>(g, cs, fr, bu, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane, true);
+#else
+      if (fr.pz + dot3(fr.n, c) - LL(L_KN_R) <= (T)0) {          // (the same test jbq_col_sphere starts with)
+        JBQ_COLD_ARGS(JBQ_BODY_U);
+        jbq_col_sphere<T>(g, cs, frc, bc, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane);
+      }
+#endif
       // upper cylinder
       gh[0] = LL(L_UC_C); gh[1] = LL(L_UC_C + 1); gh[2] = LL(L_UC_C + 2);
       sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
@@ -755,7 +787,12 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
           gv[0] = LL(L_UC_AX); gv[1] = LL(L_UC_AX + 1); gv[2] = LL(L_UC_AX + 2); mulMV(ax, R1, gv);
           gv[0] = LL(L_UC_XA); gv[1] = LL(L_UC_XA + 1); gv[2] = LL(L_UC_XA + 2); mulMV(xa, R1, gv);
-          jbq_col_cylinder<T>(g, cs, fr, bu, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+#ifdef JBQ_UPPER_INLINE
+          jbq_col_cylinder_impl<T, true>(g, cs, fr, bu, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+#else
+          JBQ_COLD_ARGS(JBQ_BODY_U);
+          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+#endif
         }
       }
     }
@@ -921,12 +958,13 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #pragma unroll
       for (int i = 0; i < 9; i++) Rg[i] = LX(X_BOX_R + i);
       QBody<T> b = {QK_ROOT, nullptr, nullptr, (T)0, nullptr, nullptr, (T)0, false, g[G_INVW0]};
-      jbq_col_box<T>(g, cs, fr, b, (int)LX(X_BOX_ID), c, Rg, half, rep, lane);
+      const QFrame<T> frc = fr;
+      jbq_col_box<T>(g, cs, frc, b, (int)LX(X_BOX_ID), c, Rg, half, rep, lane);
     }
   } else {
     const bool rotor = lane == 3;
-    QBody<T> b = {rotor ? QK_ROTOR : QK_ROOT, am, pm, rotor ? s.vm : (T)0, nullptr, nullptr, (T)0, false,
-                  rotor ? g[G_INVWM] : g[G_INVW0]};
+#define JBQ_BODY_X {rotor ? QK_ROTOR : QK_ROOT, am, pm, rotor ? s.vm : (T)0, nullptr, nullptr, (T)0, false, \
+                    rotor ? g[G_INVWM] : g[G_INVW0]}
     T ch[3] = {LX(X_CYL_C), LX(X_CYL_C + 1), LX(X_CYL_C + 2)}, c[3], r[3], t[3];
     if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
     T rr_ = LX(X_CYL_R), hl_ = LX(X_CYL_HL);
@@ -935,7 +973,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       T ax[3], xa[3];
       if (rotor) { mulMV(ax, Rm, gv); mulMV(xa, Rm, gx); }
       else { ax[0] = gv[0]; ax[1] = gv[1]; ax[2] = gv[2]; xa[0] = gx[0]; xa[1] = gx[1]; xa[2] = gx[2]; }
-      jbq_col_cylinder<T>(g, cs, fr, b, (int)LX(X_CYL_ID), c, ax, xa, rr_, hl_, rep, lane);
+      JBQ_COLD_ARGS(JBQ_BODY_X);
+      jbq_col_cylinder<T>(g, cs, frc, bc, (int)LX(X_CYL_ID), c, ax, xa, rr_, hl_, rep, lane);
     }
     ch[0] = LX(X_ELL_C); ch[1] = LX(X_ELL_C + 1); ch[2] = LX(X_ELL_C + 2);
     if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
@@ -949,7 +988,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #pragma unroll
         for (int i = 0; i < 9; i++) Rg[i] = Rh[i];
       }
-      jbq_col_ellipsoid<T>(g, cs, fr, b, (int)LX(X_ELL_ID), c, Rg, sz, rep, lane);
+      JBQ_COLD_ARGS(JBQ_BODY_X);
+      jbq_col_ellipsoid<T>(g, cs, frc, bc, (int)LX(X_ELL_ID), c, Rg, sz, rep, lane);
     }
   }
 
