@@ -40,13 +40,16 @@ JB_HD void jb_sincos_small(double x, double* s, double* c) { *s = sin(x); *c = c
 // reduction x = q pi/2 + r with a two-constant Cody-Waite split (exact for |q| < 2^10), then the classic single-precision
 // kernels on |r| <= pi/4 (errors ~1 ulp).  A few dozen branch-free instructions; the library call and its Payne-Hanek
 // slow path (bulky in the instruction stream of a kernel that is instruction-fetch bound) stay only for |x| > 100.
+// (the out-of-line fallback returns by value: handing it the caller's output pointers would pin those variables to
+// local memory on the fast path as well)
+struct JbSinCos { float s, c; };
 #if defined(__CUDACC__)
-static __host__ __device__ __noinline__ void jb_sincos_far(float x, float* s, float* c) { jb_sincos(x, s, c); }
+static __host__ __device__ __noinline__ JbSinCos jb_sincos_far(float x) { JbSinCos r; jb_sincos(x, &r.s, &r.c); return r; }
 #else
-static inline void jb_sincos_far(float x, float* s, float* c) { jb_sincos(x, s, c); }
+static inline JbSinCos jb_sincos_far(float x) { JbSinCos r; jb_sincos(x, &r.s, &r.c); return r; }
 #endif
 JB_HD void jb_sincos_fast(float x, float* s, float* c) {
-  if (fabsf(x) > 100.f) { jb_sincos_far(x, s, c); return; }
+  if (fabsf(x) > 100.f) { const JbSinCos r = jb_sincos_far(x); *s = r.s; *c = r.c; return; }
   const float q = rintf(x * 0.63661977236758134308f);
   float r = fmaf(q, -1.57079625129699707031f, x);
   r = fmaf(q, -7.54978941586159635335e-08f, r);

@@ -763,7 +763,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           jbq_col_cylinder_impl<T, true>(g, cs, fr, bl, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
 #else
           JBQ_COLD_ARGS(JBQ_BODY_L);
-          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_LC_ID), c, ax, xa, rr_, hl_, rep, lane);
+          const T cc[3] = {c[0], c[1], c[2]};
+          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_LC_ID), cc, ax, xa, rr_, hl_, rep, lane);
 #endif
         }
       }
@@ -776,7 +777,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
 #else
       if (fr.pz + dot3(fr.n, c) - LL(L_KN_R) <= (T)0) {          // (the same test jbq_col_sphere starts with)
         JBQ_COLD_ARGS(JBQ_BODY_U);
-        jbq_col_sphere<T>(g, cs, frc, bc, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane);
+        const T cc[3] = {c[0], c[1], c[2]};
+        jbq_col_sphere<T>(g, cs, frc, bc, (int)LL(L_KN_ID), cc, LL(L_KN_R), rep, lane);
       }
 #endif
       // upper cylinder
@@ -791,7 +793,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
           jbq_col_cylinder_impl<T, true>(g, cs, fr, bu, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
 #else
           JBQ_COLD_ARGS(JBQ_BODY_U);
-          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_UC_ID), c, ax, xa, rr_, hl_, rep, lane);
+          const T cc[3] = {c[0], c[1], c[2]};
+          jbq_col_cylinder<T>(g, cs, frc, bc, (int)LL(L_UC_ID), cc, ax, xa, rr_, hl_, rep, lane);
 #endif
         }
       }
@@ -959,7 +962,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       for (int i = 0; i < 9; i++) Rg[i] = LX(X_BOX_R + i);
       QBody<T> b = {QK_ROOT, nullptr, nullptr, (T)0, nullptr, nullptr, (T)0, false, g[G_INVW0]};
       const QFrame<T> frc = fr;
-      jbq_col_box<T>(g, cs, frc, b, (int)LX(X_BOX_ID), c, Rg, half, rep, lane);
+      const T cc[3] = {c[0], c[1], c[2]}, hh[3] = {half[0], half[1], half[2]};
+      jbq_col_box<T>(g, cs, frc, b, (int)LX(X_BOX_ID), cc, Rg, hh, rep, lane);
     }
   } else {
     const bool rotor = lane == 3;
@@ -974,7 +978,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       if (rotor) { mulMV(ax, Rm, gv); mulMV(xa, Rm, gx); }
       else { ax[0] = gv[0]; ax[1] = gv[1]; ax[2] = gv[2]; xa[0] = gx[0]; xa[1] = gx[1]; xa[2] = gx[2]; }
       JBQ_COLD_ARGS(JBQ_BODY_X);
-      jbq_col_cylinder<T>(g, cs, frc, bc, (int)LX(X_CYL_ID), c, ax, xa, rr_, hl_, rep, lane);
+      const T cc[3] = {c[0], c[1], c[2]};
+      jbq_col_cylinder<T>(g, cs, frc, bc, (int)LX(X_CYL_ID), cc, ax, xa, rr_, hl_, rep, lane);
     }
     ch[0] = LX(X_ELL_C); ch[1] = LX(X_ELL_C + 1); ch[2] = LX(X_ELL_C + 2);
     if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
@@ -989,7 +994,8 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
         for (int i = 0; i < 9; i++) Rg[i] = Rh[i];
       }
       JBQ_COLD_ARGS(JBQ_BODY_X);
-      jbq_col_ellipsoid<T>(g, cs, frc, bc, (int)LX(X_ELL_ID), c, Rg, sz, rep, lane);
+      const T cc[3] = {c[0], c[1], c[2]}, ss[3] = {sz[0], sz[1], sz[2]};
+      jbq_col_ellipsoid<T>(g, cs, frc, bc, (int)LX(X_ELL_ID), cc, Rg, ss, rep, lane);
     }
   }
 
