@@ -1153,9 +1153,13 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       cm.phase_sync(11);
       qv_axpy(a, alpha, search);
       qv_axpy(Ma, alpha, Mv);
-      for (int i = 0; i < cs.n; i++) {
-        QCon<T>& c = cs.c[i];
-        c.ww[0] += alpha * c.jv[0]; c.ww[1] += alpha * c.jv[1]; c.ww[2] += alpha * c.jv[2];
+      // J a - uref at the new point: only a quad that goes on iterating reads it again (a finished quad takes zero-length
+      // steps, a full step inside one active set ends the solve exactly)
+      if (!done && !full) {
+        for (int i = 0; i < cs.n; i++) {
+          QCon<T>& c = cs.c[i];
+          c.ww[0] += alpha * c.jv[0]; c.ww[1] += alpha * c.jv[1]; c.ww[2] += alpha * c.jv[2];
+        }
       }
       mask_prev = mask; full_prev = full;
       if (!done && full) { done = true; exact = true; qv_zero(grad); }
