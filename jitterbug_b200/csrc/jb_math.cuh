@@ -68,7 +68,10 @@ template <typename T> JB_HD T jb_min(T a, T b) { return a < b ? a : b; }
 template <typename T> struct JbEps;
 template <> struct JbEps<float> {
   static JB_HD float newton_tol() { return 2e-6f; }
-  static JB_HD float ls_tol() { return 1e-5f; }
+#ifndef JBQ_LS_TOL
+#define JBQ_LS_TOL 1e-5f
+#endif
+  static JB_HD float ls_tol() { return JBQ_LS_TOL; }
   static JB_HD int newton_iters() { return 16; }
 };
 template <> struct JbEps<double> {
