@@ -54,6 +54,13 @@ typedef uint32_t jbq_mask_t;
 #define JBQ_SPREAD 1
 #endif
 #define JBQ_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+// a geom close enough to the floor for its narrow phase to run is the exception: keeps those blocks out of the hot
+// instruction stream (tuning: -DJBQ_NO_UNLIKELY)
+#if defined(__CUDACC__) && !defined(JBQ_NO_UNLIKELY)
+#define JBQ_UNLIKELY(x) __builtin_expect(!!(x), 0)
+#else
+#define JBQ_UNLIKELY(x) (x)
+#endif
 
 template <typename T> struct QState {
   T pos[3], quat[4], vlin[3], w[3];     // root: replicated in the 4 lanes (MuJoCo coordinates: world linear, body angular)
@@ -753,7 +760,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       sub3(r, gh, p2h); mulMV(t, R12, r); add3(c, p2, t);
       {
         T rr_ = LL(L_LC_R), hl_ = LL(L_LC_HL);
-        if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+        if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0)) {
           gv[0] = LL(L_LC_AX); gv[1] = LL(L_LC_AX + 1); gv[2] = LL(L_LC_AX + 2); mulMV(ax, R12, gv);
           gv[0] = LL(L_LC_XA); gv[1] = LL(L_LC_XA + 1); gv[2] = LL(L_LC_XA + 2); mulMV(xa, R12, gv);
           // in line as well: a leg lying on the floor (the heavy envs) comes through here every sub-step; measured
@@ -775,7 +782,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       const QBody<T> bu = JBQ_BODY_U;
       jbq_col_sphere<T>(g, cs, fr, bu, (int)LL(L_KN_ID), c, LL(L_KN_R), rep, lane, true);
 #else
-      if (fr.pz + dot3(fr.n, c) - LL(L_KN_R) <= (T)0) {          // (the same test jbq_col_sphere starts with)
+      if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - LL(L_KN_R) <= (T)0)) {          // (the same test jbq_col_sphere starts with)
         JBQ_COLD_ARGS(JBQ_BODY_U);
         const T cc[3] = {c[0], c[1], c[2]};
         jbq_col_sphere<T>(g, cs, frc, bc, (int)LL(L_KN_ID), cc, LL(L_KN_R), rep, lane);
@@ -786,7 +793,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
       sub3(r, gh, p1); mulMV(t, R1, r); add3(c, p1, t);
       {
         T rr_ = LL(L_UC_R), hl_ = LL(L_UC_HL);
-        if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+        if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0)) {
           gv[0] = LL(L_UC_AX); gv[1] = LL(L_UC_AX + 1); gv[2] = LL(L_UC_AX + 2); mulMV(ax, R1, gv);
           gv[0] = LL(L_UC_XA); gv[1] = LL(L_UC_XA + 1); gv[2] = LL(L_UC_XA + 2); mulMV(xa, R1, gv);
 #ifdef JBQ_UPPER_INLINE
@@ -956,7 +963,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
   //                  lane 3 -> rotor cylinder + ellipsoid
   if (lane < 2) {
     T c[3] = {LX(X_BOX_C), LX(X_BOX_C + 1), LX(X_BOX_C + 2)}, half[3] = {LX(X_BOX_H), LX(X_BOX_H + 1), LX(X_BOX_H + 2)};
-    if (fr.pz + dot3(fr.n, c) - jb_sqrt(dot3(half, half)) <= (T)0) {
+    if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - jb_sqrt(dot3(half, half)) <= (T)0)) {
       T Rg[9];
 #pragma unroll
       for (int i = 0; i < 9; i++) Rg[i] = LX(X_BOX_R + i);
@@ -972,7 +979,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     T ch[3] = {LX(X_CYL_C), LX(X_CYL_C + 1), LX(X_CYL_C + 2)}, c[3], r[3], t[3];
     if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
     T rr_ = LX(X_CYL_R), hl_ = LX(X_CYL_HL);
-    if (fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0) {
+    if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - jb_sqrt(rr_ * rr_ + hl_ * hl_) <= (T)0)) {
       T gv[3] = {LX(X_CYL_AX), LX(X_CYL_AX + 1), LX(X_CYL_AX + 2)}, gx[3] = {LX(X_CYL_XA), LX(X_CYL_XA + 1), LX(X_CYL_XA + 2)};
       T ax[3], xa[3];
       if (rotor) { mulMV(ax, Rm, gv); mulMV(xa, Rm, gx); }
@@ -984,7 +991,7 @@ JB_HD void jbq_substep(Comm& cm, const T* P, int lane, QState<T>& s, T ctrl, boo
     ch[0] = LX(X_ELL_C); ch[1] = LX(X_ELL_C + 1); ch[2] = LX(X_ELL_C + 2);
     if (rotor) { sub3(r, ch, pm); mulMV(t, Rm, r); add3(c, pm, t); } else { c[0] = ch[0]; c[1] = ch[1]; c[2] = ch[2]; }
     T sz[3] = {LX(X_ELL_S), LX(X_ELL_S + 1), LX(X_ELL_S + 2)};
-    if (fr.pz + dot3(fr.n, c) - jb_max(sz[0], jb_max(sz[1], sz[2])) <= (T)0) {
+    if (JBQ_UNLIKELY(fr.pz + dot3(fr.n, c) - jb_max(sz[0], jb_max(sz[1], sz[2])) <= (T)0)) {
       T Rh[9], Rg[9];
 #pragma unroll
       for (int i = 0; i < 9; i++) Rh[i] = LX(X_ELL_R + i);

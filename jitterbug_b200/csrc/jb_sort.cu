@@ -27,6 +27,8 @@ __device__ __forceinline__ int jb_load_key(int4 ld, int n_sub, int variant) {
   const int trips = ld.w & 0xffff, last = (ld.w >> 16) & 15;
   const int extra = max(trips - n_sub, 0);                   // Newton trips beyond one per sub-step
   if (variant == 1) return min(last, 4) * 3 + min(extra, 2);
+  if (variant == 5) return min(last, 3) * 4 + min(extra, 3);
+  if (variant == 6) return min(extra, 3) * 4 + min(last, 3);
   if (variant == 2) return min((ld.x * 4 + n_sub / 2) / n_sub, 15);
   if (variant == 3) return min((ld.x * 2 + n_sub / 2) / n_sub, 6) * 2 + (extra > 0 ? 1 : 0);
   if (variant == 4) {
