@@ -230,7 +230,17 @@ template <typename T, typename Comm> JB_HD void qarrow_solve(Comm& cm, QVec<T>& 
 }
 
 // ------------------------------------------------------------------------------------------------ contacts
-// MuJoCo's solimp sigmoid (getimpedance), impedance only; si = packed solimp[5]
+// MuJoCo's solimp sigmoid (getimpedance), impedance only; si = packed solimp[5].  The general power law is a call: the
+// Jitterbug models use power = 2, and this function is inlined into every contact-creation site.
+template <typename T> JB_COLD T jbq_impedance_pow(T x, T mid, T power) {
+#if defined(__CUDA_ARCH__)
+  return x <= mid ? (T)(__powf((float)x, (float)power) / __powf((float)mid, (float)power - 1.f))
+                  : (T)(1.f - __powf(1.f - (float)x, (float)power) / __powf(1.f - (float)mid, (float)power - 1.f));
+#else
+  return x <= mid ? (T)(pow((double)x, (double)power) / pow((double)mid, (double)power - 1))
+                  : (T)(1 - pow(1 - (double)x, (double)power) / pow(1 - (double)mid, (double)power - 1));
+#endif
+}
 template <typename T> JB_HD T jbq_impedance(const T* si, T dist) {
   T d0 = jb_min((T)0.9999, jb_max((T)0.0001, si[0])), d1 = jb_min((T)0.9999, jb_max((T)0.0001, si[1]));
   T width = si[2], mid = jb_min((T)0.9999, jb_max((T)0.0001, si[3])), power = si[4];
@@ -241,16 +251,7 @@ template <typename T> JB_HD T jbq_impedance(const T* si, T dist) {
   T y;
   if (power == (T)2) y = x <= mid ? x * x / mid : (T)1 - ((T)1 - x) * ((T)1 - x) / ((T)1 - mid);
   else if (power <= (T)1) y = x;
-  else {
-#if defined(__CUDA_ARCH__)
-    // non-default solimp power: fast intrinsics keep this cold path small (the Jitterbug models use power = 2)
-    y = x <= mid ? (T)(__powf((float)x, (float)power) / __powf((float)mid, (float)power - 1.f))
-                 : (T)(1.f - __powf(1.f - (float)x, (float)power) / __powf(1.f - (float)mid, (float)power - 1.f));
-#else
-    y = x <= mid ? (T)(pow((double)x, (double)power) / pow((double)mid, (double)power - 1))
-                 : (T)(1 - pow(1 - (double)x, (double)power) / pow(1 - (double)mid, (double)power - 1));
-#endif
-  }
+  else y = jbq_impedance_pow(x, mid, power);
   return d0 + y * (d1 - d0);
 }
 
@@ -395,30 +396,29 @@ JB_HD void jbq_col_cylinder_impl(const T* g, QConSet<T>& cs, const QFrame<T>& fr
   prjaxis *= hl;
   T d1 = dist0 + prjaxis + prjvec;
   if (d1 > (T)0) return;
-  T x[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] + ax[k] - fr.n[k] * d1 * (T)0.5;
-  JBQ_EMIT_SEL(geom, x, d1);
-  T d2 = dist0 - prjaxis + prjvec;
-  if (d2 <= (T)0) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) x[k] = c[k] + vec[k] - ax[k] - fr.n[k] * d2 * (T)0.5;
-    JBQ_EMIT_SEL(geom, x, d2);
-  }
-  T d3 = dist0 + prjaxis - prjvec * (T)0.5;
+  const T d2 = dist0 - prjaxis + prjvec, d3 = dist0 + prjaxis - prjvec * (T)0.5;
+  // mjc_PlaneCylinder's up to four points -- the deepest rim point, its counterpart on the other cap, and two more on the
+  // deepest cap's rim -- are x_k = c + al_k vec + be_k ax + ga_k v1 - n d_k / 2; one loop body (one copy of the contact
+  // builder) instead of four
+  T v1[3] = {0, 0, 0};
   if (d3 <= (T)0) {
-    T v1[3];
     cross3(v1, vec, ax);
     T nn = jb_sqrt(dot3(v1, v1));
     if (nn < (T)1e-15) { v1[0] = 1; v1[1] = 0; v1[2] = 0; nn = 1; }
     T s = r * (T)0.8660254037844386 / nn;
     v1[0] *= s; v1[1] *= s; v1[2] *= s;
+  }
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 4; k++) {
+    const T dk = k == 0 ? d1 : (k == 1 ? d2 : d3);
+    if (!(dk <= (T)0)) continue;
+    const T al = k < 2 ? (T)1 : (T)-0.5, be = k == 1 ? (T)-1 : (T)1, ga = k == 2 ? (T)1 : (k == 3 ? (T)-1 : (T)0);
+    T x[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) x[k] = c[k] + v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
-    JBQ_EMIT_SEL(geom, x, d3);
-#pragma unroll
-    for (int k = 0; k < 3; k++) x[k] = c[k] - v1[k] + ax[k] - vec[k] * (T)0.5 - fr.n[k] * d3 * (T)0.5;
-    JBQ_EMIT_SEL(geom, x, d3);
+    for (int i = 0; i < 3; i++) x[i] = c[i] + al * vec[i] + be * ax[i] + ga * v1[i] - fr.n[i] * dk * (T)0.5;
+    JBQ_EMIT_SEL(geom, x, dk);
   }
 }
 
