@@ -13,7 +13,9 @@
  * part restates MuJoCo's published algorithm (Computation chapter + the open-sourced engine_*.c structure)
  * from memory and is anchored by analytic known-answer tests and an independent numpy finite-difference
  * dynamics check (tests/test_oracle_*.py); tests/test_mujoco_parity.py diffs it against a real MuJoCo
- * wherever one is importable (it skips in this project's containers).
+ * wherever one is importable (it skips in this project's containers).  The only MuJoCo-EXECUTED numbers
+ * the reference holds -- the left edge of its published PPO2 training curves (fig-rl-perf.ipynb) -- anchor it
+ * at the level of return distributions under a random policy (tests/test_published_curves.py), no finer.
  *
  * Nothing in the product path (jitterbug_b200/) links or calls this file.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it.

@@ -2,7 +2,8 @@
 
 Pinning status (see jb_oracle.h): the task layer and the heuristic policies are pinned to outputs of the reference's
 own code (tests/test_reference_golden.py); the step pipeline is PARITY UNPINNED -- no MuJoCo / dm_control in this
-image and no golden vectors in the reference.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+image and no golden vectors in the reference (its published training curves anchor return distributions under a random
+policy, tests/test_published_curves.py, nothing finer).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 may import this module; the product package ``jitterbug_b200`` never does.
 
 Besides the C step pipeline this module restates, in numpy, the reference's task layer so the CUDA task
