@@ -99,3 +99,38 @@ def test_results_do_not_depend_on_slot_order_or_segmentation():
     last = (ld[:, 3] >> 16)[perm]
     assert int(last[: n // 20].float().mean() * 100) >= int(last[-n // 20:].float().mean() * 100)
     assert envs[0].launch_count() < envs[1].launch_count()
+
+
+def test_ragged_batch_sizes_equal_the_same_envs_of_a_bigger_batch():
+    """Batches that do not fill a quad-warp, a CTA or a wave (1, 3, 97, 385 envs), and batches on either side of the size
+    from which the step is cut into load-sorted segments, give every env the trajectory it has in a bigger batch, bit for
+    bit; empty batches and wrong-length action tensors are rejected."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ref = BatchedJitterbugEnv("move_to_pose", num_envs=2048, seed=13, time_limit=0.2)      # 20-step episodes
+    want = _run(ref, 45)                                                                  # crosses two episode ends
+    for n in (1, 3, 97, 385):
+        env = BatchedJitterbugEnv("move_to_pose", num_envs=n, seed=13, time_limit=0.2)
+        env.reset()
+        for k in range(45):
+            o, r, st = env.step(_actions(2048, k, env.device)[:n])
+            assert torch.equal(o, want[k][0][:n]) and torch.equal(r, want[k][1][:n]) and torch.equal(st, want[k][2][:n]), (n, k)
+    # around the auto-sort threshold: identity order below it, sorted segments from it on
+    import ctypes as C
+    edge = 4 * 148 * 96
+    big = BatchedJitterbugEnv("move_from_origin", num_envs=edge + 5, seed=21)
+    a = _run(big, 6)
+    for n in (edge - 1, edge):
+        env = BatchedJitterbugEnv("move_from_origin", num_envs=n, seed=21)
+        env.reset()
+        for k in range(6):
+            o, r, st = env.step(_actions(edge + 5, k, env.device)[:n])
+            assert torch.equal(o, a[k][0][:n]) and torch.equal(r, a[k][1][:n]), (n, k)
+    assert big.launch_count() > 6 * 5                                    # segmented and sorted ...
+    small = BatchedJitterbugEnv("move_from_origin", num_envs=edge - 1, seed=21)
+    small.reset(); small.step(torch.zeros(edge - 1, device=small.device))
+    assert small.launch_count() <= 3                                     # ... one launch per step below the threshold
+    with pytest.raises((ValueError, RuntimeError)):
+        BatchedJitterbugEnv("move_from_origin", num_envs=0)
+    with pytest.raises(ValueError):
+        big.step(torch.zeros(7, device=big.device))
