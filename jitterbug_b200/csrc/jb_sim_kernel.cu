@@ -11,7 +11,10 @@
 // size for registers (256-thread bound: ~222 registers, no spills) and runs 256-thread CTAs.
 #ifdef JB_PER_ENV_BUILD
 #undef JB_BLOCK
-#define JB_BLOCK 256
+#ifndef JB_PERENV_BLOCK
+#define JB_PERENV_BLOCK 256
+#endif
+#define JB_BLOCK JB_PERENV_BLOCK
 #ifndef JBQ_SPREAD
 #define JBQ_SPREAD 0          /* spreading a heavy lane's contacts over its quad paid before the load sort (+3 %); with heavy
                                  envs packed into their own CTAs it costs every other CTA: 9.3 -> 10.2 M steps/s without it */
@@ -184,7 +187,11 @@ __device__ __forceinline__ void write_obs(const float* g, const JbDev& d, int e,
 
 extern __shared__ float jb_smem[];
 
+#ifdef JB_MAXNREG          /* tuning: explicit register budget instead of the one ptxas derives from the CTA size */
+__global__ void __maxnreg__(JB_MAXNREG)
+#else
 __global__ void __launch_bounds__(JB_BLOCK, JB_MIN_BLOCKS)
+#endif
 JB_SIM_KERNEL(const __grid_constant__ JbDev d, const __grid_constant__ JbLaunchArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 3;
@@ -333,8 +340,8 @@ static int jb_pick_block(int N, int per_env) {
   // Shared model: 128 threads 0.92, 256 threads 1.10, 384 threads 1.28 -- large batches want the 384-thread CTA (lowest
   // cost per env), small ones (e.g. the 4096-env parity configuration) smaller CTAs that spread over more SMs.
   // Per-env models (the JB_PER_ENV_BUILD instantiation): 128 threads 0.78, 192 threads 1.05, 256 threads 1.31.
-  const int cand[2][3] = {{384, 256, 128}, {256, 192, 128}};
-  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {1.31f, 1.05f, 0.78f}};
+  const int cand[2][3] = {{384, 256, 128}, {JB_BLOCK, 192, 128}};
+  const float tcta[2][3] = {{1.28f, 1.10f, 0.92f}, {1.31f * JB_BLOCK / 256, 1.05f, 0.78f}};
   const int m = per_env ? 1 : 0;
   int threads = 128;
   float best = 1e30f;
