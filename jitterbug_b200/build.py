@@ -20,9 +20,11 @@ LIB = os.path.join(LIBDIR, "libjbsim.so")
 UNITS = [("jb_sim_kernel.cu", "jb_sim_kernel", []), ("jb_sim_kernel.cu", "jb_sim_kernel_perenv", ["-DJB_PER_ENV_BUILD"]),
          ("jb_api.cu", "jb_api", []), ("jb_sort.cu", "jb_sort", []), ("jb_monitor.cu", "jb_monitor", []), ("jb_encoder.cu", "jb_encoder", []), ("jb_augment.cu", "jb_augment", [])]
 # -prec-div/-prec-sqrt=false: 2-ulp reciprocal-based division instead of the IEEE slow path (bulky and not needed at the
-# 1e-5 parity tolerance); sin/cos stay the accurate versions (no --use_fast_math).
+# 1e-5 parity tolerance); -ftz=true: fp32 denormals flush to zero, which drops the denormal-scaling wrappers around the
+# reciprocal / rsqrt sequences (-3 % instructions, +3 % throughput; no physical quantity here lives near 1e-38);
+# sin/cos stay the accurate versions (no --use_fast_math).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + \
+              "-prec-div=false", "-prec-sqrt=false", "-ftz=true", "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + \
     os.environ.get("JB_NVCC_EXTRA", "").split()
 
 
