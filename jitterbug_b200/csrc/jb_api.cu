@@ -379,6 +379,8 @@ int jb_sim_step(JbSim* s, const float* actions_dev, float* obs_dev, float* rewar
     if (cur == 1) CUDA_TRY(cudaMemcpyAsync(s->perm_buf, s->perm_buf + N, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
     s->d.perm = s->perm_buf;
   }
+  // the period is counted on the host: a CUDA graph captured from this call replays the monitor on every step or on none,
+  // whichever the captured step did (it only feeds counters[5..7], never the simulation)
   if (s->monitor && (s->steps++ % JB_MONITOR_PERIOD) == 0) {
     CUDA_TRY(jb_launch_self_clearance(s->d, nullptr, st));
     s->launches++;
