@@ -396,3 +396,17 @@ def test_self_clearance_monitor_matches_numpy_and_stays_positive(compiled_model)
         prox = {gg: cover(gg) for gg in moving}
         want = min(pair_clearance(prox[a], prox[b]) for a, b in pairs)
         assert abs(clr[e] - want) < 2e-6, (e, clr[e], want)
+
+
+def test_ppo_example_runs_end_to_end():
+    """examples/ppo_train.py (collection through the CUDA-graph path + clipped-surrogate updates) keeps working: a few
+    iterations with short episodes, finite returns, summary line printed."""
+    import json, os, subprocess, sys
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "examples", "ppo_train.py"), "--task", "face_direction", "--envs", "512",
+                          "--horizon", "16", "--iters", "4", "--minibatches", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    last = json.loads(out.stdout.strip().splitlines()[-1])
+    assert last["env_steps"] == 4 * 16 * 512 and last["diverged_resets"] == 0 and last["collect_steps_per_s"] > 0
