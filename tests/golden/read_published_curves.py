@@ -70,13 +70,42 @@ def digitise():
     return out
 
 
+def digitise_over_training(step_px=8):
+    """The whole PPO2 curve of move_from_origin and move_in_direction: [episode index / 1000, median, p10, p90] every
+    ``step_px`` pixel columns (45 episodes).  During training the policy of these two panels does not improve (the
+    paper reports PPO2 failing on them); what changes is mostly its std, so the curve traces a one-parameter family of
+    (median, p10, p90) triples that a simulator can be asked to reproduce for SOME std at every point."""
+    from PIL import Image
+    im = np.asarray(Image.open(io.BytesIO(figure_png())).convert("RGB")).astype(int)
+    dist = lambda rgb: np.abs(im - np.array(rgb)).sum(2)
+    curve = dist((31, 119, 180)) < 120
+    band = (dist((214, 222, 236)) < 10) | (dist((233, 241, 248)) < 8)
+    out = {}
+    x0 = X0_COL["ppo2"]
+    for task in ("move_from_origin", "move_in_direction"):
+        p = TASKS.index(task)
+        val = lambda row: 1000.0 - (row - Y1000_ROW[p]) / PX_PER_UNIT
+        r0, r1 = int(Y1000_ROW[p] - 30), int(Y1000_ROW[p] + PX_PER_UNIT * 1050 + 5)
+        rows = []
+        for x in range(x0 + 12, x0 + 900, step_px):
+            cr = np.where(curve[r0:r1, x])[0]
+            br = np.where((band | curve)[r0:r1, x])[0]
+            if len(cr) == 0:
+                break                                   # the curve ends (runs were stopped at different lengths)
+            rows.append([round((x - x0) / 177.4, 3), round(float(val(cr.mean() + r0)), 1),
+                         round(float(val(br.max() + r0)), 1), round(float(val(br.min() + r0)), 1)])
+        out[task] = rows
+    return out
+
+
 def main():
     data = dict(
         source="fig-rl-perf.ipynb, cell 2, image/png output (2165 x 2921 px), digitised by tests/golden/read_published_curves.py",
         meaning="per-episode return percentiles over all monitor files, 20-episode moving average, first ~80 episodes",
         policy="ppo2: stable-baselines PPO2 at initialisation = clip(N(0,1), -1, 1) per control step; ddpg: trains from step 256, not a fixed policy",
         reading_error=5.0,
-        curves=digitise())
+        curves=digitise(),
+        ppo2_over_training=digitise_over_training())
     path = os.path.join(HERE, "published_training_start.json")
     with open(path, "w") as f:
         json.dump(data, f, indent=1)

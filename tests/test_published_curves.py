@@ -41,9 +41,13 @@ BANDS = {
 }
 
 
-def _published():
+def _fixture():
     with open(os.path.join(HERE, "golden", "published_training_start.json")) as f:
-        return json.load(f)["curves"]
+        return json.load(f)
+
+
+def _published():
+    return _fixture()["curves"]
 
 
 def _report(task, ret, pub, where):
@@ -74,8 +78,8 @@ def test_fixture_matches_the_reference_figure():
     pytest.importorskip("PIL")
     sys.path.insert(0, os.path.join(HERE, "golden"))
     import read_published_curves as R
-    got = R.digitise()
-    assert got == _published()
+    assert R.digitise() == _published()
+    assert R.digitise_over_training() == _fixture()["ppo2_over_training"]
 
 
 @pytest.mark.parametrize("task", ["move_from_origin", "move_in_direction"])
@@ -124,6 +128,20 @@ def test_cuda_random_policy_returns_match_the_published_curves(task):
     _check(task, _cuda_returns(task, 1.0), "cuda")
 
 
+SIGMAS = (1.0, 1.25, 1.5, 1.75, 2.0, 2.5, 3.0, 4.0, 6.0)
+_FAMILY = {}
+
+
+def _family(task):
+    """sigma -> (median, p10, p90) of the per-episode return on the CUDA path (4096 episodes each), cached per module."""
+    if task not in _FAMILY:
+        _FAMILY[task] = {}
+        for sigma in SIGMAS:
+            ret = _cuda_returns(task, sigma, M=4096)
+            _FAMILY[task][sigma] = tuple(float(np.quantile(ret, q)) for q in (.5, .1, .9))
+    return _FAMILY[task]
+
+
 @pytest.mark.gpu
 def test_cuda_one_policy_std_reproduces_all_published_percentiles():
     """The first plotted point already averages the first ~20 episodes of every monitor file, 1.6e5 environment steps
@@ -136,11 +154,10 @@ def test_cuda_one_policy_std_reproduces_all_published_percentiles():
     tasks = ("move_from_origin", "move_in_direction")
     tol = dict(median=0.06, p90=0.03, p10=50.0)            # relative, relative, absolute return units
     table, ok = {}, []
-    for sigma in (1.0, 1.25, 1.5, 1.75, 2.0, 2.5):
+    for sigma in SIGMAS[:6]:
         good, row = True, []
         for task in tasks:
-            ret, p = _cuda_returns(task, sigma), pub[f"{task}/ppo2"]
-            med, p10, p90 = (float(np.quantile(ret, q)) for q in (.5, .1, .9))
+            (med, p10, p90), p = _family(task)[sigma], pub[f"{task}/ppo2"]
             row += [med, p10, p90]
             good &= abs(med - p["median"]) <= tol["median"] * p["median"] and abs(p90 - p["p90"]) <= tol["p90"] * p["p90"] \
                 and abs(p10 - p["p10"]) <= tol["p10"]
@@ -152,3 +169,34 @@ def test_cuda_one_policy_std_reproduces_all_published_percentiles():
     print("published      : mfo median/p10/p90 " + " ".join(f"{pub[f'{t}/ppo2'][k]:6.1f}" for t in tasks for k in ("median", "p10", "p90")))
     assert ok, table
     assert all(1.25 <= s_ <= 2.5 for s_ in ok), ok
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task,p10_tol", [("move_from_origin", 100.0), ("move_in_direction", 60.0)])
+def test_cuda_std_family_traces_the_published_ppo2_curves(task, p10_tol):
+    """PPO2 never learns these two tasks in the paper; over its 2-3.5e6 training steps the plotted (median, p10, p90)
+    drifts (move_from_origin: 826/206/954 -> 423/78/918) the way a zero-mean policy of growing std does.  Every
+    published point whose median lies inside the range our sigma family spans must then have the family's p10 and p90 at
+    that median (interpolated in sigma): a relation between the percentiles that does not need sigma(t).  It checks the
+    structure of the return distribution (permanent tip-overs at a constant hazard on top of a narrow "upright" mode),
+    not a single number.  Loose bands -- p10 within 100 / 60 return units at every point and within 60 % of that on
+    average, p90 within 6 % --: the published percentiles come from 40-80 episodes per point, and PPO2's policy mean
+    moves as well.  Measured: our p10 sits below the published one at equal median (by ~ 50 on move_from_origin, ~ 22 on
+    move_in_direction), i.e. the published "upright" mode is ~ 4 % lower than ours, the same offset the sigma = 1.75
+    fit of the first point shows."""
+    _need_gpu()
+    fam = _family(task)
+    pts = np.array([fam[s_] for s_ in SIGMAS if s_ >= 1.5])             # medians fall monotonically from sigma = 1.5 on
+    order = np.argsort(pts[:, 0])
+    med, p10, p90 = pts[order].T
+    assert np.all(np.diff(med) > 0)
+    curve = np.array(_fixture()["ppo2_over_training"][task])
+    inside = curve[(curve[:, 1] >= med[0]) & (curve[:, 1] <= med[-1])]
+    assert len(inside) >= 0.7 * len(curve), (len(inside), len(curve), med[0], med[-1])
+    d10 = np.interp(inside[:, 1], med, p10) - inside[:, 2]
+    d90 = np.interp(inside[:, 1], med, p90) / inside[:, 3] - 1.0
+    print(f"{task}: {len(inside)} of {len(curve)} published points inside the family's median range [{med[0]:.0f}, {med[-1]:.0f}]; "
+          f"p10 ours - published: mean {d10.mean():+.1f}, worst {np.abs(d10).max():.1f}; p90 relative: mean {d90.mean():+.4f}, "
+          f"worst {np.abs(d90).max():.4f}")
+    assert np.abs(d10).max() <= p10_tol and abs(d10.mean()) <= 0.6 * p10_tol
+    assert np.abs(d90).max() <= 0.06
