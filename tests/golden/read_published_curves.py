@@ -20,6 +20,7 @@ import base64
 import io
 import json
 import os
+import re
 
 import numpy as np
 
@@ -107,8 +108,10 @@ def main():
         curves=digitise(),
         ppo2_over_training=digitise_over_training())
     path = os.path.join(HERE, "published_training_start.json")
+    text = json.dumps(data, indent=1)
+    text = re.sub(r"\[\s*(-?[\d.]+),\s*(-?[\d.]+),\s*(-?[\d.]+),\s*(-?[\d.]+)\s*\]", r"[\1, \2, \3, \4]", text)   # one row per line
     with open(path, "w") as f:
-        json.dump(data, f, indent=1)
+        f.write(text + "\n")
     print(path)
     for k, v in data["curves"].items():
         print(f"  {k:28s} median {v['median']:6.1f}  p10 {v['p10']:6.1f}  p90 {v['p90']:6.1f}  usable {v['usable']}")
