@@ -13,6 +13,7 @@
 #ifndef JBSIM_H
 #define JBSIM_H
 
+#include <stddef.h>
 #include <stdint.h>
 #include "../jitterbug_b200/csrc/jb_model.h"
 
@@ -81,6 +82,17 @@ int jb_sim_heuristic_actions(JbSim* sim, const float* obs_dev, float* actions_de
  * Row-major [num_envs][16|15|15] device buffers, MuJoCo ordering.  NULL pointers are skipped. */
 int jb_sim_get_state(JbSim* sim, float* qpos_dev, float* qvel_dev, float* warm_dev, void* stream);
 int jb_sim_set_state(JbSim* sim, const float* qpos_dev, const float* qvel_dev, const float* warm_dev, void* stream);
+
+/* Exact checkpoint / resume of the episode state (the reference checkpoints the agent only,
+ * benchmark.py:234-237; an env has no state file -- a batched simulator needs one).  The blob holds everything
+ * jb_sim_step reads and writes per env: positions with the motor angle in its wrapped + revolution-counter form,
+ * velocities, warm start, target pose, step count, episode index (which keys the Philox stream of the next reset) and the
+ * pending-reset flag; a simulator created with the same config, models and tasks and restored from it continues bit
+ * for bit, through episode boundaries.  jb_sim_get_state / jb_sim_set_state are the MuJoCo-layout interchange (fp32
+ * motor angle, no RNG state) and are not exact in that sense.  `blob_dev`: jb_sim_snapshot_size(sim) bytes on the device. */
+size_t jb_sim_snapshot_size(const JbSim* sim);
+int jb_sim_snapshot(JbSim* sim, void* blob_dev, void* stream);
+int jb_sim_restore(JbSim* sim, const void* blob_dev, void* stream);
 /* target pose per env: [num_envs][4] = x, y, quat_w, quat_z (model.body_pos / body_quat["target"], jitterbug.py:613-648) */
 int jb_sim_get_target(JbSim* sim, float* target_dev, void* stream);
 int jb_sim_set_target(JbSim* sim, const float* target_dev, void* stream);

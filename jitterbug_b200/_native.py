@@ -77,6 +77,9 @@ SYMBOLS = {
                                 C.c_uint64, _P]),
     "jb_sim_num_envs": (C.c_int, [_P]),
     "jb_sim_launch_count": (C.c_ulonglong, [_P]),
+    "jb_sim_snapshot_size": (C.c_size_t, [_P]),
+    "jb_sim_snapshot": (C.c_int, [_P, C.c_void_p, C.c_void_p]),
+    "jb_sim_restore": (C.c_int, [_P, C.c_void_p, C.c_void_p]),
     "jb_sim_obs_stride": (C.c_int, [_P]),
     "jb_last_error": (C.c_char_p, []),
     "jb_version": (C.c_char_p, []),

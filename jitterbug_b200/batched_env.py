@@ -254,6 +254,20 @@ class BatchedJitterbugEnv:
             _native.check(self._lib.jb_sim_set_step_count(self._h, C.c_void_p(c.data_ptr()), self._stream()))
         torch.cuda.current_stream(self.device).synchronize()
 
+    def snapshot(self) -> torch.Tensor:
+        """Exact checkpoint of the episode state of every env (uint8 device tensor): positions incl. the motor's
+        revolution counter, velocities, warm start, targets, step counts, episode indices (the reset RNG key) and pending
+        resets.  ``restore`` on an env built with the same arguments continues bit for bit."""
+        blob = torch.empty(int(self._lib.jb_sim_snapshot_size(self._h)), dtype=torch.uint8, device=self.device)
+        _native.check(self._lib.jb_sim_snapshot(self._h, C.c_void_p(blob.data_ptr()), self._stream()))
+        return blob
+
+    def restore(self, blob: torch.Tensor) -> None:
+        if blob.dtype != torch.uint8 or blob.device != self.device or not blob.is_contiguous() \
+                or blob.numel() != int(self._lib.jb_sim_snapshot_size(self._h)):
+            raise ValueError("blob must be the contiguous uint8 tensor snapshot() returned for an env of this size and device")
+        _native.check(self._lib.jb_sim_restore(self._h, C.c_void_p(blob.data_ptr()), self._stream()))
+
     def get_target(self) -> torch.Tensor:
         t = torch.empty(self.num_envs, 4, device=self.device)
         _native.check(self._lib.jb_sim_get_target(self._h, C.c_void_p(t.data_ptr()), self._stream()))

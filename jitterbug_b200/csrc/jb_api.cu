@@ -495,6 +495,47 @@ int jb_sim_set_step_count(JbSim* s, const int32_t* count_dev, void* stream) {
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
+// ---- exact checkpoint / resume: the per-env arrays of JbDev that a step reads and writes, back to back in one blob
+struct SnapPart { void* p; size_t bytes; };
+static int snap_parts(JbSim* s, SnapPart* out) {
+  const size_t N = s->d.N;
+  JbDev& d = s->d;
+  const SnapPart parts[] = {{d.qpos, 16 * N * sizeof(float)}, {d.qvel, 15 * N * sizeof(float)}, {d.warm, 15 * N * sizeof(float)},
+                            {d.target, 4 * N * sizeof(float)}, {d.rev, N * sizeof(int)}, {d.step_count, N * sizeof(int)},
+                            {d.episode, N * sizeof(int)}, {d.reset_next, N}};
+  const int n = (int)(sizeof(parts) / sizeof(parts[0]));
+  for (int i = 0; i < n; i++) out[i] = parts[i];
+  return n;
+}
+size_t jb_sim_snapshot_size(const JbSim* s) {
+  if (!s) return 0;
+  SnapPart parts[8];
+  const int n = snap_parts(const_cast<JbSim*>(s), parts);
+  size_t total = 0;
+  for (int i = 0; i < n; i++) total += (parts[i].bytes + 15) & ~(size_t)15;
+  return total;
+}
+static int snap_copy(JbSim* s, char* blob, bool restore, cudaStream_t st) {
+  SnapPart parts[8];
+  const int n = snap_parts(s, parts);
+  size_t off = 0;
+  for (int i = 0; i < n; i++) {
+    if (restore) CUDA_TRY(cudaMemcpyAsync(parts[i].p, blob + off, parts[i].bytes, cudaMemcpyDeviceToDevice, st));
+    else CUDA_TRY(cudaMemcpyAsync(blob + off, parts[i].p, parts[i].bytes, cudaMemcpyDeviceToDevice, st));
+    off += (parts[i].bytes + 15) & ~(size_t)15;
+  }
+  return 0;
+}
+int jb_sim_snapshot(JbSim* s, void* blob_dev, void* stream) {
+  if (!s || !blob_dev) return fail("jb_sim_snapshot: null argument");
+  JB_GUARD(s);
+  return snap_copy(s, (char*)blob_dev, false, (cudaStream_t)stream);
+}
+int jb_sim_restore(JbSim* s, const void* blob_dev, void* stream) {
+  if (!s || !blob_dev) return fail("jb_sim_restore: null argument");
+  JB_GUARD(s);
+  return snap_copy(s, (char*)const_cast<void*>(blob_dev), true, (cudaStream_t)stream);
+}
 int jb_sim_get_contacts(JbSim* s, int32_t* ncon_dev, int32_t* geom_dev, float* dist_dev, int max_con, void* stream) {
   if (!s || !ncon_dev || !geom_dev || !dist_dev || max_con <= 0) return fail("jb_sim_get_contacts: bad argument");
   JB_GUARD(s);
